@@ -1,0 +1,152 @@
+/*
+ * s2_cuda.h — C ABI of libs2cuda.so: the B200 (sm_100a) renderer for synth2's hot path
+ * (oscillator -> filter -> envelope -> mix, s2_lib/src/try3/{process,synth}.rs).
+ *
+ * The reference has no FFI of its own: its boundary is the public Rust API of
+ * `s2_lib::try3`.  Each entry point below names the reference item it replaces; INTEGRATION.md
+ * shows the `extern "C"` block and the safe Rust wrapper (`Synth::new/note_on/note_off/sample`
+ * with the reference's signatures) that a maintainer adds to s2_lib to switch the path over.
+ *
+ * Conventions: plain pointers and sizes only; every call returns S2_OK (0) or a negative
+ * S2_ERR_* code and records a message readable through s2_last_error(); no exception crosses
+ * the boundary.  A handle is not thread-safe (same contract as `&mut self` in the reference).
+ * There is NO CPU fallback: without a CUDA device every compute entry fails with
+ * S2_ERR_NO_DEVICE / S2_ERR_CUDA.
+ */
+#ifndef S2_CUDA_H
+#define S2_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2_ABI_VERSION 1u
+
+enum {
+    S2_OK = 0,
+    S2_ERR_INVALID = -1,     /* bad argument (null handle, misaligned buffer, bad enum, ...) */
+    S2_ERR_NO_DEVICE = -2,   /* no CUDA device / device index out of range */
+    S2_ERR_CUDA = -3,        /* a CUDA runtime call or kernel failed; see s2_last_error() */
+    S2_ERR_OVERFLOW = -4,    /* frame offset would pass u32::MAX (reference panics: process.rs:36,71) */
+    S2_ERR_NOMEM = -5
+};
+
+/* static_config.rs:25-31 `OscillatorKind`, declaration order */
+enum { S2_OSC_SQUARE = 0, S2_OSC_SAW = 1, S2_OSC_TRIANGLE = 2, S2_OSC_SINE = 3 };
+
+/* Voice filter.  ONE_POLE is the live reference filter (filters.rs:15-34, driven per sample at
+   process.rs:363-371).  BIQUAD_LP is `SecondOrderLowPassFilter` (dsp_filters.rs:82-130), which
+   the reference declares but never calls; it is offered for BASELINE config 3. */
+enum { S2_FILTER_ONE_POLE = 0, S2_FILTER_BIQUAD_LP = 1 };
+
+#define S2_NO_RELEASE 0xFFFFFFFFu /* release_frame_offset == None (synth.rs:28; simdtest.rs:283) */
+
+/*
+ * One voice = one `sc::Layer` patch (static_config.rs:3-44) + the per-voice fields of
+ * `synth::Voice` (synth.rs:23-30).  Times in milliseconds, frequencies in Hz, exactly the
+ * reference's units (units.rs:1-17).  80 bytes, no padding.
+ */
+typedef struct s2_voice_desc {
+    uint32_t osc_kind;            /* sc::Oscillator.kind */
+    uint32_t noise_seed;          /* st::NoiseState.seed (state.rs:17-21; Synth always uses 0) */
+    float pitch_hz;               /* note_to_pitch(note), synth.rs:208-212; see s2_note_to_pitch */
+    float osc_gain;               /* sc::Oscillator.gain  (ADDED in the x16 path, process.rs:341-345) */
+    float noise_amt;              /* sc::Layer.noise      (ADDED in the x16 path, process.rs:353-356) */
+    float lpf_freq_hz;            /* sc::LowPassFilter.freq */
+    float damping;                /* BIQUAD_LP only: damping_factor, dsp_filters.rs:94-96 */
+    float amp_attack_ms, amp_decay_ms, amp_sustain, amp_release_ms; /* sc::Layer.amp_env */
+    float mod_attack_ms, mod_decay_ms, mod_sustain, mod_release_ms; /* sc::Layer.mod_env */
+    float mod_env_to_osc_freq;    /* sc::Modulations, Bipolar<10> */
+    float mod_env_to_lpf_freq;
+    uint32_t frame_offset;        /* Voice.current_frame_offset at the first rendered frame */
+    uint32_t release_offset;      /* Voice.release_frame_offset or S2_NO_RELEASE */
+    uint32_t active;              /* current_frame_offset.is_some(); 0 = silent, not advanced */
+} s2_voice_desc;
+
+/* Carried DSP state of one voice: st::Layer (state.rs:8-21) + Voice.current_frame_offset.
+   This is what crosses buffer boundaries; get/set it to checkpoint or migrate a bank. 32 bytes. */
+typedef struct s2_voice_state {
+    float phase;            /* OscillatorState.phase_accum value (oscillators.rs:402-406) */
+    uint32_t has_phase;     /* ... and its Option discriminant (None renders as phase 0.0, process.rs:316) */
+    uint32_t frame_offset;  /* advances by `frames` per render, saturating (synth.rs:197) */
+    float lpf_last;         /* LowPassFilterState.last (filters.rs:3-7) */
+    float x1, x2, y1, y2;   /* SecondOrderLowPassFilterState (dsp_filters.rs:74-80) */
+} s2_voice_state;
+
+typedef struct s2_bank s2_bank;   /* V independent voices resident on one GPU */
+typedef struct s2_synth s2_synth; /* mirror of synth::Synth (synth.rs:9-12): 8 voices, default patch */
+
+/* ---- library ---- */
+uint32_t s2_abi_version(void);
+const char* s2_last_error(void);          /* thread-local, never NULL */
+int s2_device_count(int* count);
+
+/* synth.rs:208-212 `note_to_pitch` (host libm powf, the same call the reference makes) */
+float s2_note_to_pitch(uint8_t note);
+/* synth.rs:125-152 `Synth::default_config()` as a voice description (inactive, offset 0) */
+void s2_default_voice(s2_voice_desc* out);
+
+/* ---- voice bank: the batched form of process::process_layer_buf_simd (process.rs:14-49) ---- */
+
+/* Uploads `n_voices` descriptions to GPU `device`; `stream` is a cudaStream_t (NULL = default
+   stream) on which all work of this bank is enqueued. */
+int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_t n_voices,
+                   const s2_voice_desc* voices, void* stream, s2_bank** out);
+void s2_bank_destroy(s2_bank* bank);
+size_t s2_bank_voices(const s2_bank* bank);
+
+/* Replace one voice (note_on into slot `index`, synth.rs:61-70: fresh state, offset from desc). */
+int s2_bank_set_voice(s2_bank* bank, size_t index, const s2_voice_desc* voice);
+/* note_off for slot `index` (synth.rs:72-80): release_frame_offset = current_frame_offset. */
+int s2_bank_release_voice(s2_bank* bank, size_t index);
+
+/*
+ * Render `frames` frames of every active voice, process_layer_buf_simd semantics per voice
+ * (x16 blocks, then `frames % 16` scalar-path tail frames), and advance the carried state.
+ *   d_voice_out  device pointer or NULL; row v = d_voice_out + v*row_stride, `frames` floats;
+ *                16-byte aligned base and row_stride % 4 == 0.  Inactive voices write zeros.
+ *   d_bus_out    device pointer or NULL; `frames` floats, mono (audio_player.rs:23-24):
+ *                bus[i] = sum over voices in index order (synth.rs:176-202).  For banks of up
+ *                to 32 voices the order is exactly the reference's; above, per-warp partial
+ *                sums (each in index order) are added in warp order.
+ * Asynchronous on the bank's stream.
+ */
+int s2_bank_render(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_stride,
+                   float* d_bus_out);
+
+/* Same, then copies the bus to HOST memory and synchronises the stream (Synth::sample shape). */
+int s2_bank_render_bus_host(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_stride,
+                            float* h_bus_out);
+
+/* Checkpoint / restore / test hook.  Host arrays of n_voices entries; synchronises. */
+int s2_bank_get_state(s2_bank* bank, s2_voice_state* out);
+int s2_bank_set_state(s2_bank* bank, const s2_voice_state* in);
+int s2_bank_sync(s2_bank* bank);
+
+/* Debug tap for parity of discrete quantities: renders like s2_bank_render with no output but
+   records, per voice and frame, the oscillator phase used for that frame (x16 frames only). */
+int s2_bank_trace_phase(s2_bank* bank, size_t frames, float* d_phase_out, size_t row_stride);
+
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+   `gpu_launches`). */
+uint64_t s2_launch_count(void);
+
+/* ---- Synth mirror (synth.rs:53-203) ---- */
+int s2_synth_new(int device, s2_synth** out);                         /* Synth::new()  synth.rs:54-59 */
+void s2_synth_free(s2_synth* synth);
+int s2_synth_note_on(s2_synth* synth, uint8_t note, float velocity);  /* synth.rs:61-70 */
+int s2_synth_note_off(s2_synth* synth, uint8_t note);                 /* synth.rs:72-80; returns 1 on "released twice" */
+/* Synth::sample(&mut self, buffer: &mut [f32], sample_rate) synth.rs:154-169: overwrites
+   `frames` floats of HOST memory with the mono mix of the 8 voices. */
+int s2_synth_sample(s2_synth* synth, float* h_buffer, size_t frames, uint32_t sample_rate);
+/* test hook: slot contents; returns 1 if the slot has a current_frame_offset, 0 if free */
+int s2_synth_voice_info(s2_synth* synth, int slot, uint8_t* note, uint32_t* current_offset,
+                        uint32_t* release_offset, s2_voice_state* state);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,110 @@
+"""ctypes binding of libs2cuda.so — the C ABI in include/s2_cuda.h, nothing more.
+
+There is no fallback: if the library is missing this module raises at import of the symbol
+table, and every compute entry fails with an error from the library when no GPU is present.
+"""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG / "libs2cuda.so"
+
+S2_OK = 0
+S2_ERR_INVALID = -1
+S2_ERR_NO_DEVICE = -2
+S2_ERR_CUDA = -3
+S2_ERR_OVERFLOW = -4
+S2_ERR_NOMEM = -5
+
+OSC_SQUARE, OSC_SAW, OSC_TRIANGLE, OSC_SINE = 0, 1, 2, 3
+FILTER_ONE_POLE, FILTER_BIQUAD_LP = 0, 1
+NO_RELEASE = 0xFFFFFFFF
+
+# struct s2_voice_desc (80 bytes) / s2_voice_state (32 bytes), include/s2_cuda.h
+VOICE_DESC = np.dtype([
+    ("osc_kind", "<u4"), ("noise_seed", "<u4"), ("pitch_hz", "<f4"), ("osc_gain", "<f4"),
+    ("noise_amt", "<f4"), ("lpf_freq_hz", "<f4"), ("damping", "<f4"),
+    ("amp_attack_ms", "<f4"), ("amp_decay_ms", "<f4"), ("amp_sustain", "<f4"), ("amp_release_ms", "<f4"),
+    ("mod_attack_ms", "<f4"), ("mod_decay_ms", "<f4"), ("mod_sustain", "<f4"), ("mod_release_ms", "<f4"),
+    ("mod_env_to_osc_freq", "<f4"), ("mod_env_to_lpf_freq", "<f4"),
+    ("frame_offset", "<u4"), ("release_offset", "<u4"), ("active", "<u4"),
+])
+VOICE_STATE = np.dtype([
+    ("phase", "<f4"), ("has_phase", "<u4"), ("frame_offset", "<u4"), ("lpf_last", "<f4"),
+    ("x1", "<f4"), ("x2", "<f4"), ("y1", "<f4"), ("y2", "<f4"),
+])
+assert VOICE_DESC.itemsize == 80 and VOICE_STATE.itemsize == 32
+
+# every symbol include/s2_cuda.h declares: (restype, argtypes)
+_vp, _sz, _u32, _u8, _f, _i = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint8, C.c_float, C.c_int
+SYMBOLS = {
+    "s2_abi_version": (_u32, []),
+    "s2_last_error": (C.c_char_p, []),
+    "s2_device_count": (_i, [C.POINTER(_i)]),
+    "s2_note_to_pitch": (_f, [_u8]),
+    "s2_default_voice": (None, [_vp]),
+    "s2_bank_create": (_i, [_i, _u32, _u32, _sz, _vp, _vp, C.POINTER(_vp)]),
+    "s2_bank_destroy": (None, [_vp]),
+    "s2_bank_voices": (_sz, [_vp]),
+    "s2_bank_set_voice": (_i, [_vp, _sz, _vp]),
+    "s2_bank_release_voice": (_i, [_vp, _sz]),
+    "s2_bank_render": (_i, [_vp, _sz, _vp, _sz, _vp]),
+    "s2_bank_render_bus_host": (_i, [_vp, _sz, _vp, _sz, _vp]),
+    "s2_bank_get_state": (_i, [_vp, _vp]),
+    "s2_bank_set_state": (_i, [_vp, _vp]),
+    "s2_bank_sync": (_i, [_vp]),
+    "s2_bank_trace_phase": (_i, [_vp, _sz, _vp, _sz]),
+    "s2_launch_count": (C.c_uint64, []),
+    "s2_synth_new": (_i, [_i, C.POINTER(_vp)]),
+    "s2_synth_free": (None, [_vp]),
+    "s2_synth_note_on": (_i, [_vp, _u8, _f]),
+    "s2_synth_note_off": (_i, [_vp, _u8]),
+    "s2_synth_sample": (_i, [_vp, _vp, _sz, _u32]),
+    "s2_synth_voice_info": (_i, [_vp, _i, C.POINTER(_u8), C.POINTER(_u32), C.POINTER(_u32), _vp]),
+}
+
+
+class S2Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libs2cuda error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads libs2cuda.so once.  Raises if it has not been built (python -m synth2_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m synth2_b200.build` "
+                              "(the renderer has no CPU or PyTorch fallback)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise S2Error(rc, lib().s2_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def ptr(a):
+    """Address of a numpy array / torch tensor / int / None as a c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))

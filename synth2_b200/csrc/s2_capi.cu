@@ -1,0 +1,576 @@
+// s2_capi.cu — host side of libs2cuda.so: the C ABI declared in include/s2_cuda.h.
+//
+// Two objects:
+//   s2_bank  — V voices resident on one GPU (SoA parameters + carried state), rendered by
+//              s2::launch_render; the batched form of process::process_layer_buf_simd.
+//   s2_synth — mirror of synth::Synth (s2_lib/src/try3/synth.rs): 8 voice slots, the default
+//              patch, oldest-voice allocation, note_on / note_off / sample.  The voice bookkeeping
+//              runs on the host exactly like the reference's; only rendering goes to the GPU.
+// No CPU rendering exists in this library.
+#include "../../include/s2_cuda.h"
+#include "s2_internal.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(S2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+bool finite_nonneg(float x) { return std::isfinite(x) && x >= 0.0f; }
+
+int validate_voice(const s2_voice_desc& d, size_t index) {
+    if (d.osc_kind > S2_OSC_SINE) return fail(S2_ERR_INVALID, "voice %zu: osc_kind %u", index, d.osc_kind);
+    if (!(std::isfinite(d.pitch_hz) && d.pitch_hz > 0.0f))
+        return fail(S2_ERR_INVALID, "voice %zu: pitch_hz must be finite and > 0", index);
+    if (!(std::isfinite(d.lpf_freq_hz) && d.lpf_freq_hz >= 0.0f))
+        return fail(S2_ERR_INVALID, "voice %zu: lpf_freq_hz must be finite and >= 0", index);
+    const float ms[6] = {d.amp_attack_ms, d.amp_decay_ms, d.amp_release_ms,
+                         d.mod_attack_ms, d.mod_decay_ms, d.mod_release_ms};
+    for (float m : ms)
+        if (!finite_nonneg(m)) return fail(S2_ERR_INVALID, "voice %zu: envelope times must be finite and >= 0", index);
+    const float fl[7] = {d.osc_gain, d.noise_amt, d.damping, d.amp_sustain, d.mod_sustain,
+                         d.mod_env_to_osc_freq, d.mod_env_to_lpf_freq};
+    for (float f : fl)
+        if (!std::isfinite(f)) return fail(S2_ERR_INVALID, "voice %zu: non-finite parameter", index);
+    return S2_OK;
+}
+
+uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+float ubits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+void pack_voice(const s2_voice_desc& d, float* col, size_t pitch) {
+    using namespace s2;
+    col[P_KIND * pitch] = ubits(d.osc_kind);
+    col[P_SEED * pitch] = ubits(d.noise_seed);
+    col[P_PITCH * pitch] = d.pitch_hz;
+    col[P_GAIN * pitch] = d.osc_gain;
+    col[P_NOISE * pitch] = d.noise_amt;
+    col[P_LPF * pitch] = d.lpf_freq_hz;
+    col[P_DAMP * pitch] = d.damping;
+    col[P_AA * pitch] = d.amp_attack_ms;
+    col[P_AD * pitch] = d.amp_decay_ms;
+    col[P_AS * pitch] = d.amp_sustain;
+    col[P_AR * pitch] = d.amp_release_ms;
+    col[P_MA * pitch] = d.mod_attack_ms;
+    col[P_MD * pitch] = d.mod_decay_ms;
+    col[P_MS * pitch] = d.mod_sustain;
+    col[P_MR * pitch] = d.mod_release_ms;
+    col[P_AMT_OSC * pitch] = d.mod_env_to_osc_freq;
+    col[P_AMT_LPF * pitch] = d.mod_env_to_lpf_freq;
+    col[P_RELEASE * pitch] = ubits(d.release_offset);
+    col[P_ACTIVE * pitch] = ubits(d.active ? 1u : 0u);
+}
+
+void pack_state(const s2_voice_state& s, float* col, size_t pitch) {
+    using namespace s2;
+    col[S_PHASE * pitch] = s.phase;
+    col[S_HAS_PHASE * pitch] = ubits(s.has_phase ? 1u : 0u);
+    col[S_OFFSET * pitch] = ubits(s.frame_offset);
+    col[S_LAST * pitch] = s.lpf_last;
+    col[S_X1 * pitch] = s.x1;
+    col[S_X2 * pitch] = s.x2;
+    col[S_Y1 * pitch] = s.y1;
+    col[S_Y2 * pitch] = s.y2;
+}
+
+struct VoiceBook {           // host mirror of what the device will hold, O(1) per render
+    uint32_t start_offset;   // frame offset when the voice was (re)started
+    uint64_t start_total;    // bank->total_frames at that moment
+    uint32_t active;
+    uint32_t osc_kind;
+};
+
+}  // namespace
+
+struct s2_bank {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t sample_rate = 0;
+    uint32_t filter_kind = 0;
+    size_t n_voices = 0;
+    size_t vpad = 0;
+    float* d_params = nullptr;
+    float* d_state = nullptr;
+    float* d_partials = nullptr;
+    size_t partials_cap = 0;     // floats
+    float* d_bus = nullptr;
+    size_t bus_cap = 0;          // floats
+    std::vector<VoiceBook> book;
+    uint64_t total_frames = 0;
+    uint64_t max_offset = 0;     // upper bound of any active voice's frame offset
+    size_t n_sine = 0;
+};
+
+namespace {
+
+uint32_t current_offset(const s2_bank* b, size_t i) {
+    const VoiceBook& vb = b->book[i];
+    if (!vb.active) return vb.start_offset;
+    const uint64_t o = (uint64_t)vb.start_offset + (b->total_frames - vb.start_total);
+    return o > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)o;   // saturating_add, synth.rs:197
+}
+
+int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out,
+                     int trace) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    if (frames == 0) return S2_OK;
+    if (frames > 0x7FFFFFFFull) return fail(S2_ERR_INVALID, "frames %zu too large for one call", frames);
+    if (d_voice_out) {
+        if (((uintptr_t)d_voice_out & 15u) != 0 || (row_stride & 3u) != 0 || row_stride < frames)
+            return fail(S2_ERR_INVALID, "voice_out must be 16-byte aligned with row_stride %% 4 == 0 and >= frames");
+    }
+    if (b->max_offset + frames > 0xFFFFFFFFull)
+        return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
+    CUDA_TRY(cudaSetDevice(b->device));
+
+    const uint32_t n_warps = (uint32_t)((b->n_voices + 31) / 32);
+    float* partials = nullptr;
+    if (d_bus_out) {
+        if (n_warps == 1) {
+            partials = d_bus_out;   // a single warp sums its voices in index order: that IS the bus
+        } else {
+            const size_t need = (size_t)n_warps * frames;
+            if (need > b->partials_cap) {
+                if (b->d_partials) CUDA_TRY(cudaFree(b->d_partials));
+                b->d_partials = nullptr; b->partials_cap = 0;
+                CUDA_TRY(cudaMalloc(&b->d_partials, need * sizeof(float)));
+                b->partials_cap = need;
+            }
+            partials = b->d_partials;
+        }
+    }
+
+    s2::RenderArgs a;
+    a.params = b->d_params;
+    a.state = b->d_state;
+    a.n_voices = (uint32_t)b->n_voices;
+    a.vpad = (uint32_t)b->vpad;
+    a.sample_rate = (float)b->sample_rate;
+    a.frames = (uint32_t)frames;
+    a.voice_out = d_voice_out;
+    a.row_stride = row_stride;
+    a.bus_partials = partials;
+    a.has_sine = b->n_sine ? 1u : 0u;
+    CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (d_bus_out && n_warps > 1) {
+        CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, d_bus_out, b->stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    b->total_frames += frames;
+    b->max_offset += frames;
+    return S2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t s2_abi_version(void) { return S2_ABI_VERSION; }
+const char* s2_last_error(void) { return g_err; }
+uint64_t s2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int s2_device_count(int* count) {
+    if (!count) return fail(S2_ERR_INVALID, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(S2_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return S2_OK;
+}
+
+// synth.rs:208-212
+float s2_note_to_pitch(uint8_t note) {
+    const float n = (float)note;
+    return 440.0f * powf(2.0f, (n - 69.0f) / 12.0f);
+}
+
+// synth.rs:125-152
+void s2_default_voice(s2_voice_desc* d) {
+    if (!d) return;
+    memset(d, 0, sizeof *d);
+    d->osc_kind = S2_OSC_SAW;
+    d->noise_seed = 0;
+    d->pitch_hz = 440.0f;
+    d->osc_gain = 1.0f;
+    d->noise_amt = 0.0f;
+    d->lpf_freq_hz = 200.0f;
+    d->damping = 1.41421356f;
+    d->amp_attack_ms = 100.0f; d->amp_decay_ms = 100.0f; d->amp_sustain = 0.5f; d->amp_release_ms = 100.0f;
+    d->mod_attack_ms = 0.0f; d->mod_decay_ms = 200.0f; d->mod_sustain = 0.0f; d->mod_release_ms = 0.0f;
+    d->mod_env_to_osc_freq = 0.0f;
+    d->mod_env_to_lpf_freq = 10.0f;
+    d->frame_offset = 0;
+    d->release_offset = S2_NO_RELEASE;
+    d->active = 0;
+}
+
+int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_t n_voices,
+                   const s2_voice_desc* voices, void* stream, s2_bank** out) {
+    if (!out) return fail(S2_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (n_voices == 0 || !voices) return fail(S2_ERR_INVALID, "empty bank");
+    if (n_voices > 0x7FFFFFE0ull) return fail(S2_ERR_INVALID, "too many voices");
+    if (sample_rate == 0) return fail(S2_ERR_INVALID, "sample_rate must be > 0");
+    if (filter_kind > S2_FILTER_BIQUAD_LP) return fail(S2_ERR_INVALID, "filter_kind %u", filter_kind);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(S2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(S2_ERR_NO_DEVICE, "device %d out of range (%d)", device, ndev);
+    for (size_t i = 0; i < n_voices; i++) {
+        int rc = validate_voice(voices[i], i);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+
+    s2_bank* b = new (std::nothrow) s2_bank;
+    if (!b) return fail(S2_ERR_NOMEM, "out of host memory");
+    b->device = device;
+    b->stream = (cudaStream_t)stream;
+    b->sample_rate = sample_rate;
+    b->filter_kind = filter_kind;
+    b->n_voices = n_voices;
+    b->vpad = (n_voices + 31) & ~(size_t)31;
+    b->book.resize(n_voices);
+
+    std::vector<float> hp((size_t)s2::P_COUNT * b->vpad, 0.0f), hs((size_t)s2::S_COUNT * b->vpad, 0.0f);
+    for (size_t i = 0; i < n_voices; i++) {
+        pack_voice(voices[i], hp.data() + i, b->vpad);
+        s2_voice_state st;
+        memset(&st, 0, sizeof st);
+        st.frame_offset = voices[i].frame_offset;
+        pack_state(st, hs.data() + i, b->vpad);
+        b->book[i] = {voices[i].frame_offset, 0, voices[i].active ? 1u : 0u, voices[i].osc_kind};
+        if (voices[i].active && voices[i].frame_offset > b->max_offset) b->max_offset = voices[i].frame_offset;
+        if (voices[i].osc_kind == S2_OSC_SINE) b->n_sine++;
+    }
+    cudaError_t e = cudaMalloc(&b->d_params, hp.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_state, hs.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_params, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_state, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) {
+        int rc = fail(e == cudaErrorMemoryAllocation ? S2_ERR_NOMEM : S2_ERR_CUDA, "bank upload: %s", cudaGetErrorString(e));
+        s2_bank_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return S2_OK;
+}
+
+void s2_bank_destroy(s2_bank* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_params);
+    cudaFree(b->d_state);
+    cudaFree(b->d_partials);
+    cudaFree(b->d_bus);
+    delete b;
+}
+
+size_t s2_bank_voices(const s2_bank* b) { return b ? b->n_voices : 0; }
+
+int s2_bank_set_voice(s2_bank* b, size_t index, const s2_voice_desc* voice) {
+    if (!b || !voice) return fail(S2_ERR_INVALID, "null argument");
+    if (index >= b->n_voices) return fail(S2_ERR_INVALID, "voice index %zu out of range", index);
+    int rc = validate_voice(*voice, index);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(b->device));
+    float hp[s2::P_COUNT], hs[s2::S_COUNT];
+    pack_voice(*voice, hp, 1);
+    s2_voice_state st;
+    memset(&st, 0, sizeof st);            // st::Layer::default(), synth.rs:68
+    st.frame_offset = voice->frame_offset;
+    pack_state(st, hs, 1);
+    // one 4-byte element per SoA row
+    CUDA_TRY(cudaMemcpy2DAsync(b->d_params + index, b->vpad * sizeof(float), hp, sizeof(float), sizeof(float),
+                               s2::P_COUNT, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(b->d_state + index, b->vpad * sizeof(float), hs, sizeof(float), sizeof(float),
+                               s2::S_COUNT, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));   // hp/hs live on this stack frame
+    if (b->book[index].osc_kind == S2_OSC_SINE) b->n_sine--;
+    if (voice->osc_kind == S2_OSC_SINE) b->n_sine++;
+    b->book[index] = {voice->frame_offset, b->total_frames, voice->active ? 1u : 0u, voice->osc_kind};
+    if (voice->active && voice->frame_offset > b->max_offset) b->max_offset = voice->frame_offset;
+    return S2_OK;
+}
+
+int s2_bank_release_voice(s2_bank* b, size_t index) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    if (index >= b->n_voices) return fail(S2_ERR_INVALID, "voice index %zu out of range", index);
+    CUDA_TRY(cudaSetDevice(b->device));
+    const uint32_t rel = current_offset(b, index);   // release_frame_offset = current_frame_offset (synth.rs:75)
+    CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad + index, &rel, sizeof rel,
+                             cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+int s2_bank_render(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out) {
+    return bank_render_impl(b, frames, d_voice_out, row_stride, d_bus_out, s2::TRACE_NONE);
+}
+
+int s2_bank_trace_phase(s2_bank* b, size_t frames, float* d_phase_out, size_t row_stride) {
+    if (!d_phase_out) return fail(S2_ERR_INVALID, "null phase_out");
+    return bank_render_impl(b, frames, d_phase_out, row_stride, nullptr, s2::TRACE_PHASE);
+}
+
+int s2_bank_render_bus_host(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* h_bus_out) {
+    if (!b || !h_bus_out) return fail(S2_ERR_INVALID, "null argument");
+    if (frames == 0) return S2_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (frames > b->bus_cap) {
+        if (b->d_bus) CUDA_TRY(cudaFree(b->d_bus));
+        b->d_bus = nullptr; b->bus_cap = 0;
+        CUDA_TRY(cudaMalloc(&b->d_bus, frames * sizeof(float)));
+        b->bus_cap = frames;
+    }
+    int rc = bank_render_impl(b, frames, d_voice_out, row_stride, b->d_bus, s2::TRACE_NONE);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_bus_out, b->d_bus, frames * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+int s2_bank_get_state(s2_bank* b, s2_voice_state* out) {
+    if (!b || !out) return fail(S2_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->device));
+    std::vector<float> hs((size_t)s2::S_COUNT * b->vpad);
+    CUDA_TRY(cudaMemcpyAsync(hs.data(), b->d_state, hs.size() * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    const size_t p = b->vpad;
+    for (size_t i = 0; i < b->n_voices; i++) {
+        s2_voice_state& s = out[i];
+        s.phase = hs[s2::S_PHASE * p + i];
+        s.has_phase = fbits(hs[s2::S_HAS_PHASE * p + i]);
+        s.frame_offset = fbits(hs[s2::S_OFFSET * p + i]);
+        s.lpf_last = hs[s2::S_LAST * p + i];
+        s.x1 = hs[s2::S_X1 * p + i];
+        s.x2 = hs[s2::S_X2 * p + i];
+        s.y1 = hs[s2::S_Y1 * p + i];
+        s.y2 = hs[s2::S_Y2 * p + i];
+    }
+    return S2_OK;
+}
+
+int s2_bank_set_state(s2_bank* b, const s2_voice_state* in) {
+    if (!b || !in) return fail(S2_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->device));
+    std::vector<float> hs((size_t)s2::S_COUNT * b->vpad, 0.0f);
+    uint64_t mx = 0;
+    for (size_t i = 0; i < b->n_voices; i++) {
+        pack_state(in[i], hs.data() + i, b->vpad);
+        b->book[i].start_offset = in[i].frame_offset;
+        b->book[i].start_total = b->total_frames;
+        if (b->book[i].active && in[i].frame_offset > mx) mx = in[i].frame_offset;
+    }
+    b->max_offset = mx;
+    CUDA_TRY(cudaMemcpyAsync(b->d_state, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+int s2_bank_sync(s2_bank* b) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Synth mirror (s2_lib/src/try3/synth.rs)
+
+namespace {
+constexpr int kNumVoices = 8;   // synth.rs:7
+
+struct SynthVoice {             // synth.rs:23-30 (DSP state lives on the device)
+    uint8_t note = 0;
+    float velocity = 0.0f;      // stored, never read by the DSP (synth.rs:26)
+    bool has_current = false;
+    bool has_release = false;
+    uint32_t release = 0;
+};
+}  // namespace
+
+struct s2_synth {
+    int device = 0;
+    s2_bank* bank = nullptr;    // created by the first sample() call, which is when the rate is known
+    uint32_t sample_rate = 0;
+    SynthVoice voices[kNumVoices];
+    // note events that arrived before the bank exists
+    s2_voice_desc pending[kNumVoices];
+    bool dirty[kNumVoices] = {};
+};
+
+namespace {
+
+uint32_t synth_current(const s2_synth* s, int i) {
+    if (!s->voices[i].has_current) return 0xFFFFFFFFu;   // unwrap_or(u32::MAX), synth.rs:106-107
+    if (s->bank && !s->dirty[i]) return current_offset(s->bank, (size_t)i);
+    return s->pending[i].frame_offset;
+}
+
+int synth_flush(s2_synth* s) {
+    for (int i = 0; i < kNumVoices; i++) {
+        if (!s->dirty[i]) continue;
+        int rc = s2_bank_set_voice(s->bank, (size_t)i, &s->pending[i]);
+        if (rc) return rc;
+        s->dirty[i] = false;
+    }
+    return S2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int s2_synth_new(int device, s2_synth** out) {
+    if (!out) return fail(S2_ERR_INVALID, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(S2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(S2_ERR_NO_DEVICE, "device %d out of range (%d)", device, ndev);
+    s2_synth* s = new (std::nothrow) s2_synth;
+    if (!s) return fail(S2_ERR_NOMEM, "out of host memory");
+    s->device = device;
+    for (int i = 0; i < kNumVoices; i++) s2_default_voice(&s->pending[i]);   // Voice::default(): free slot
+    *out = s;
+    return S2_OK;
+}
+
+void s2_synth_free(s2_synth* s) {
+    if (!s) return;
+    s2_bank_destroy(s->bank);
+    delete s;
+}
+
+// synth.rs:61-70 + next_voice :101-120: the first slot with the strictly greatest offset; free = u32::MAX
+int s2_synth_note_on(s2_synth* s, uint8_t note, float velocity) {
+    if (!s) return fail(S2_ERR_INVALID, "null synth");
+    int oldest = 0;
+    for (int i = 1; i < kNumVoices; i++)
+        if (synth_current(s, i) > synth_current(s, oldest)) oldest = i;
+    SynthVoice& v = s->voices[oldest];
+    v.note = note;
+    v.velocity = velocity;
+    v.has_current = true;
+    v.has_release = false;
+    v.release = 0;
+    s2_voice_desc d;
+    s2_default_voice(&d);
+    d.pitch_hz = s2_note_to_pitch(note);
+    d.frame_offset = 0;
+    d.release_offset = S2_NO_RELEASE;
+    d.active = 1;
+    s->pending[oldest] = d;
+    s->dirty[oldest] = true;
+    return S2_OK;
+}
+
+// synth.rs:72-99: the LAST active voice holding that note
+int s2_synth_note_off(s2_synth* s, uint8_t note) {
+    if (!s) return fail(S2_ERR_INVALID, "null synth");
+    int found = -1;
+    for (int i = 0; i < kNumVoices; i++) {
+        const SynthVoice& v = s->voices[i];
+        if (v.note == note && v.has_current && !v.has_release) found = i;
+    }
+    if (found < 0) return S2_OK;
+    SynthVoice& v = s->voices[found];
+    v.has_release = true;
+    v.release = synth_current(s, found);
+    if (s->dirty[found] || !s->bank) {
+        s->pending[found].release_offset = v.release;
+        s->dirty[found] = true;
+        return S2_OK;
+    }
+    return s2_bank_release_voice(s->bank, (size_t)found);
+}
+
+int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample_rate) {
+    if (!s || (!h_buffer && frames)) return fail(S2_ERR_INVALID, "null argument");
+    if (frames == 0) return S2_OK;
+    if (s->bank && s->sample_rate != sample_rate) {
+        // The reference takes the rate per call (synth.rs:156).  Changing it mid-stream re-derives
+        // every rate-dependent constant; carry the DSP state over into a bank built for the new rate.
+        std::vector<s2_voice_state> st(kNumVoices);
+        std::vector<s2_voice_desc> ds(kNumVoices);
+        int rc = s2_bank_get_state(s->bank, st.data());
+        if (rc) return rc;
+        for (int i = 0; i < kNumVoices; i++) {
+            ds[i] = s->pending[i];
+            if (!s->dirty[i]) ds[i].frame_offset = st[i].frame_offset;
+        }
+        s2_bank* nb = nullptr;
+        rc = s2_bank_create(s->device, sample_rate, S2_FILTER_ONE_POLE, kNumVoices, ds.data(), nullptr, &nb);
+        if (rc) return rc;
+        for (int i = 0; i < kNumVoices; i++)
+            if (s->dirty[i]) { memset(&st[i], 0, sizeof st[i]); st[i].frame_offset = ds[i].frame_offset; }
+        rc = s2_bank_set_state(nb, st.data());
+        if (rc) { s2_bank_destroy(nb); return rc; }
+        s2_bank_destroy(s->bank);
+        s->bank = nb;
+        s->sample_rate = sample_rate;
+        for (int i = 0; i < kNumVoices; i++) s->dirty[i] = false;
+    }
+    if (!s->bank) {
+        int rc = s2_bank_create(s->device, sample_rate, S2_FILTER_ONE_POLE, kNumVoices, s->pending, nullptr, &s->bank);
+        if (rc) return rc;
+        s->sample_rate = sample_rate;
+        for (int i = 0; i < kNumVoices; i++) s->dirty[i] = false;
+    }
+    int rc = synth_flush(s);
+    if (rc) return rc;
+    return s2_bank_render_bus_host(s->bank, frames, nullptr, 0, h_buffer);
+}
+
+int s2_synth_voice_info(s2_synth* s, int slot, uint8_t* note, uint32_t* current_offset_out,
+                        uint32_t* release_offset, s2_voice_state* state) {
+    if (!s || slot < 0 || slot >= kNumVoices) return fail(S2_ERR_INVALID, "bad slot");
+    const SynthVoice& v = s->voices[slot];
+    if (note) *note = v.note;
+    if (current_offset_out) *current_offset_out = synth_current(s, slot);
+    if (release_offset) *release_offset = v.has_release ? v.release : S2_NO_RELEASE;
+    if (state) {
+        memset(state, 0, sizeof *state);
+        if (s->bank && !s->dirty[slot]) {
+            std::vector<s2_voice_state> st(kNumVoices);
+            int rc = s2_bank_get_state(s->bank, st.data());
+            if (rc) return rc;
+            *state = st[slot];
+        }
+    }
+    return v.has_current ? 1 : 0;
+}
+
+}  // extern "C"

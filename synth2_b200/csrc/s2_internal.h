@@ -1,0 +1,50 @@
+// s2_internal.h — shared between the kernels (s2_kernels.cu) and the C-ABI host layer (s2_capi.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace s2 {
+
+// Device-resident voice parameters: struct-of-arrays, row k at params[k * vpad + v], so the 32
+// lanes of a warp (= 32 consecutive voices) load each field with one coalesced request.
+// u32 fields are stored as raw bits in the float array.
+enum ParamIdx {
+    P_KIND = 0, P_SEED, P_PITCH, P_GAIN, P_NOISE, P_LPF, P_DAMP,
+    P_AA, P_AD, P_AS, P_AR,   // amp ADSR (ms, ms, level, ms)
+    P_MA, P_MD, P_MS, P_MR,   // mod ADSR
+    P_AMT_OSC, P_AMT_LPF,
+    P_RELEASE, P_ACTIVE,
+    P_COUNT
+};
+
+// Carried state, same layout: state[k * vpad + v].
+enum StateIdx { S_PHASE = 0, S_HAS_PHASE, S_OFFSET, S_LAST, S_X1, S_X2, S_Y1, S_Y2, S_COUNT };
+
+enum TraceMode { TRACE_NONE = 0, TRACE_PHASE = 1 };
+
+struct RenderArgs {
+    const float* params;   // [P_COUNT][vpad]
+    float* state;          // [S_COUNT][vpad]
+    uint32_t n_voices;
+    uint32_t vpad;
+    float sample_rate;     // `sample_rate.0 as f32` (filters.rs:17, units.rs:21)
+    uint32_t frames;       // frames to render this launch
+    float* voice_out;      // [n_voices][row_stride] or nullptr
+    size_t row_stride;
+    float* bus_partials;   // [n_warps][frames] or nullptr
+    uint32_t has_sine;     // any voice uses the table oscillator -> stage SIN_TABLE in smem
+};
+
+constexpr int kWarpsPerBlock = 1;
+constexpr int kChunk = 32;          // frames per warp tile
+constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, conflict-free STS.128/LDS.128
+
+// Launchers (s2_kernels.cu).  Return the cudaError_t of the launch.
+cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream);
+cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* bus,
+                              cudaStream_t stream);
+cudaError_t upload_sin_table();     // copies the table into __device__ memory of the current device
+
+}  // namespace s2

@@ -1,0 +1,290 @@
+"""Pins the CPU oracle against every known-answer the reference holds for this path
+(SURVEY.md section 8c): the 4 `#[test]` functions of s2_lib and the notebook prototype values,
+plus derived known-answers computed from the reference definitions (labelled *derived*)."""
+import pathlib
+
+import numpy as np
+import pytest
+
+import oracle
+
+L = oracle.lib()
+NONE = oracle.NO_RELEASE
+
+
+def f32(x):
+    return np.float32(x)
+
+
+# ---- hashnoise.rs:70-98 -------------------------------------------------------------------
+
+def test_hash_word_scalar_equals_x16():
+    """hashnoise.rs:70-83 `test_hash_word`."""
+    start = np.full(16, 0xFF00FF00, dtype=np.uint32)
+    word = np.full(16, 0x11111111, dtype=np.uint32)
+    out = np.zeros(16, dtype=np.uint32)
+    L.s2o_hash_word_x16(start.ctypes.data, word.ctypes.data, out.ctypes.data)
+    h = L.s2o_hash_word(0xFF00FF00, 0x11111111)
+    assert h == out[0]
+    assert h == 0xB1BDD11E  # derived
+
+
+def test_hash_word_dist():
+    """hashnoise.rs:85-98 `test_hash_word_dist`: sum of popcounts over 200,004 hashes == count * 16."""
+    count = 200004
+    ones = sum(bin(L.s2o_hash_word(0, i)).count("1") for i in range(count))
+    assert ones == count * 16 == 3200064
+
+
+def test_hash_matches_numpy_restatement():
+    i = np.arange(200004, dtype=np.uint64)
+    h = (i * np.uint64(0x9E3779B9)) & np.uint64(0xFFFFFFFF)   # rotl(0,5) ^ i == i
+    probe = [0, 1, 2, 77, 65535, 65536, 200003]
+    for p in probe:
+        assert L.s2o_hash_word(0, p) == int(h[p])
+
+
+# ---- lookup.rs:250-310 --------------------------------------------------------------------
+
+@pytest.mark.parametrize("x16", [1, 0])
+def test_table_lookup(x16):
+    """lookup.rs:250-279 `test_table_lookup` (x16) and :281-310 `test_table_lookup_x16` (scalar)."""
+    t4 = np.array([0, 1, 2, 3], dtype=np.float32)
+    t5 = np.array([0, 1, 2, 3, 4], dtype=np.float32)
+    ex = lambda v: L.s2o_table_lookup_exclusive(t4.ctypes.data, 4, v, 4.0, x16)
+    inc = lambda v: L.s2o_table_lookup_inclusive(t5.ctypes.data, 5, v, 4.0, x16)
+    assert ex(0.0) == 0.0
+    assert ex(0.5) == 0.5
+    assert ex(3.5) == 1.5      # wraps to index 0
+    assert inc(0.0) == 0.0
+    assert inc(0.5) == 0.5
+    assert inc(3.0) == 3.0
+    assert inc(4.0) == 4.0
+
+
+# ---- Untitled.ipynb cells 2 and 4 (f64 prototype; weak known answers) --------------------------
+
+@pytest.mark.parametrize("fn", ["s2o_adsr_x16_lane", "s2o_adsr_scalar"])
+def test_notebook_adsr(fn):
+    adsr = getattr(L, fn)
+    assert adsr(1.0, 100.0, 0.5, 1.0, 10, NONE) == pytest.approx(0.955, abs=1e-6)
+    got = [adsr(0.0, 10.0, 0.0, 10.0, n, 30) for n in range(40)]
+    want = [1.0 - 0.1 * n for n in range(10)] + [0.0] * 30
+    assert got == pytest.approx(want, abs=1e-6)
+
+
+def test_notebook_modulate_freq():
+    env = [L.s2o_adsr_x16_lane(0.0, 10.0, 0.0, 10.0, n, 30) for n in range(12)]
+    got = [L.s2o_modulate_freq(100.0, e, 1.0) for e in env]
+    want = [200.0, 186.6066, 174.1101, 162.4505, 151.5717, 141.4214, 131.9508, 123.1144, 114.8698,
+            107.1773, 100.0, 100.0]
+    assert got == pytest.approx(want, rel=2e-6)
+
+
+# ---- derived known answers (computed from the reference definitions) ---------------------------
+
+def test_units_derived():
+    assert L.s2o_ms_as_samples(100.0, 48000) == 4800.0
+    assert L.s2o_ms_as_samples(200.0, 48000) == 9600.0
+    assert L.s2o_hz_as_samples(440.0, 48000) == f32(48000.0) / f32(440.0)
+    assert L.s2o_note_to_pitch(69) == 440.0
+    assert L.s2o_note_to_pitch(81) == 880.0
+    assert L.s2o_note_to_pitch(57) == 220.0
+
+
+def test_one_pole_coefficient_derived():
+    # *derived*, independently in numpy: t = ((-2*pi)*200)/48000 in f32 steps, k = RN32(exp(t))
+    import math
+    t = f32(f32(f32(-2.0) * f32(math.pi)) * f32(200.0)) / f32(48000.0)
+    k = L.s2o_lpf_coeff(200.0, 48000)
+    assert f32(k) == f32(math.exp(float(t)))
+    assert k == pytest.approx(0.9741598, abs=3e-8)
+    assert f32(1.0) - f32(k) == pytest.approx(0.025840223, abs=1e-9)
+    last = np.zeros(1, dtype=np.float32)
+    y = L.s2o_lpf_process(last.ctypes.data, 48000, 200.0, 1.0)
+    assert y == last[0] == f32(1.0) - f32(k)
+
+
+def test_noise_range_and_fast_form_is_exact():
+    """value/65535*2-1 spans exactly [-1, 1]; the kernel's division-free form equals it for every
+    possible 16-bit hash value (seed 0: the low 16 bits of n*K are a bijection of n's low 16)."""
+    seen = set()
+    lo, hi = 1.0, -1.0
+    for n in range(65536):
+        a = L.s2o_hash_noise(0, float(n))
+        b = L.s2o_noise_fast_form(0, n)
+        assert np.float32(a).tobytes() == np.float32(b).tobytes()
+        seen.add(L.s2o_hash_word(0, n) & 0xFFFF)
+        lo, hi = min(lo, a), max(hi, a)
+    assert len(seen) == 65536
+    assert lo == -1.0 and hi == 1.0
+
+
+def test_noise_differs_from_reciprocal_multiply():
+    """*derived* (SURVEY 8c): v * (1/65535) differs from the IEEE quotient at 512 of 65,536 inputs and
+    the final noise sample at 191 of them — the reason the kernel may not use a plain reciprocal."""
+    v = np.arange(65536, dtype=np.float32)
+    q = v / np.float32(65535.0)
+    r = v * (np.float32(1.0) / np.float32(65535.0))
+    assert int(np.count_nonzero(q != r)) == 512
+    two, one = np.float32(2.0), np.float32(1.0)
+    assert int(np.count_nonzero((q * two - one) != (r * two - one))) == 191
+
+
+def test_phased_offset_never_reaches_period():
+    """RN(period * phase) < period for phase < 1: `offset % period` is a no-op on the x16 path."""
+    rng = np.random.default_rng(7)
+    P = rng.uniform(1.0, 4096.0, 400000).astype(np.float32)
+    ph = np.nextafter(np.float32(1.0), np.float32(0.0)) - rng.integers(0, 64, 400000).astype(np.float32) * np.float32(2.0 ** -24)
+    ph = np.concatenate([ph, rng.uniform(0, 1, 400000).astype(np.float32)])
+    P = np.concatenate([P, P])
+    x = P * ph   # one f32 rounding, same as fma(P, ph, 0)
+    assert np.all(x < P)
+    assert np.all(np.fmod(x, P) == x)
+
+
+def test_osc_shapes():
+    P = f32(100.0)
+    assert L.s2o_osc_sample(1, P, 0.0, 1) == 1.0                 # saw starts at +1
+    assert L.s2o_osc_sample(1, P, 0.5, 1) == pytest.approx(0.0, abs=1e-6)
+    assert L.s2o_osc_sample(0, P, 0.25, 1) == 1.0                # square high half
+    assert L.s2o_osc_sample(0, P, 0.5, 1) == -1.0
+    assert L.s2o_osc_sample(2, P, 0.0, 1) == 1.0                 # triangle +1 -> -1 -> +1
+    assert L.s2o_osc_sample(2, P, 0.5, 1) == pytest.approx(-1.0, abs=1e-6)
+    assert L.s2o_osc_sample(3, P, 0.25, 1) == pytest.approx(1.0, abs=1e-6)   # sine table
+    assert L.s2o_osc_sample(3, P, 0.0, 1) == 0.0
+
+
+def test_accum_phase_wraps():
+    p = f32(0.0)
+    period = f32(48000.0) / f32(440.0)
+    for _ in range(2000):
+        p = L.s2o_accum_phase(p, period)
+        assert 0.0 <= p < 1.0
+
+
+def test_sin_table_matches_reference_data():
+    ref = pathlib.Path("/root/reference/components/s2_lib/src/try3/tables.rs")
+    tab = oracle.sin_table()
+    assert tab.shape == (1024,)
+    assert tab[0] == 0.0
+    assert tab.view(np.uint32)[512] == 0xB3BBBD2E    # -8.742278e-08, not 0 (tables.rs:514)
+    if not ref.exists():
+        pytest.skip("reference tree not mounted (GPU box)")
+    import re
+    vals = re.findall(r"^\s*(-?\d+\.\d+),\s*$", ref.read_text(), re.M)
+    want = np.array([np.float32(v) for v in vals], dtype=np.float32)
+    assert want.tobytes() == tab.tobytes()
+
+
+def test_sin_table_copies_identical():
+    root = pathlib.Path(__file__).resolve().parent.parent
+    a = (root / "oracle" / "sin_table_bits.inc").read_text()
+    b = (root / "synth2_b200" / "csrc" / "sin_table_bits.inc").read_text()
+    assert a == b
+
+
+# ---- x16 vs scalar divergences --------------------------------------------------
+
+def test_x16_adds_gain_scalar_multiplies():
+    cfg = oracle.default_config()
+    st = np.zeros(1, dtype=oracle.LAYER_STATE)
+    out16 = np.zeros(16, dtype=np.float32)
+    L.s2o_process_layer_x16(cfg.ctypes.data, st.ctypes.data, 440.0, 48000, 4800, NONE, out16.ctypes.data)
+    st2 = np.zeros(1, dtype=oracle.LAYER_STATE)
+    sc = L.s2o_process_layer(cfg.ctypes.data, st2.ctypes.data, 440.0, 48000, 4800, NONE)
+    # first sample: saw(phase 0) = 1; x16 input = (1 + 1) + (nz + 0), scalar input = 1*1 + nz*0
+    assert out16[0] != sc
+
+
+def test_x16_release_waits_for_sustain_scalar_does_not():
+    # release during attack: x16 keeps attacking (release clamped to A+D), scalar releases at once
+    a16 = L.s2o_adsr_x16_lane(100.0, 100.0, 0.5, 100.0, 60, 50)
+    asc = L.s2o_adsr_scalar(100.0, 100.0, 0.5, 100.0, 60, 50)
+    assert a16 == pytest.approx(0.6, abs=1e-6)
+    assert asc == pytest.approx(0.5 * (1 - 10 / 100), abs=1e-6)
+
+
+def test_buf_simd_splits_x16_and_tail():
+    cfg = oracle.default_config()
+    st = np.zeros(1, dtype=oracle.LAYER_STATE)
+    buf = np.zeros(37, dtype=np.float32)
+    assert L.s2o_process_layer_buf_simd(cfg.ctypes.data, st.ctypes.data, 440.0, 48000, 0, NONE, buf.ctypes.data, 37) == 0
+    st2 = np.zeros(1, dtype=oracle.LAYER_STATE)
+    a = np.zeros(16, dtype=np.float32)
+    b = np.zeros(16, dtype=np.float32)
+    L.s2o_process_layer_x16(cfg.ctypes.data, st2.ctypes.data, 440.0, 48000, 0, NONE, a.ctypes.data)
+    L.s2o_process_layer_x16(cfg.ctypes.data, st2.ctypes.data, 440.0, 48000, 16, NONE, b.ctypes.data)
+    tail = [L.s2o_process_layer(cfg.ctypes.data, st2.ctypes.data, 440.0, 48000, 32 + i, NONE) for i in range(5)]
+    assert buf[:16].tobytes() == a.tobytes() and buf[16:32].tobytes() == b.tobytes()
+    assert buf[32:].tolist() == tail
+    assert st.tobytes() == st2.tobytes()
+
+
+def test_buf_simd_overflow_is_an_error():
+    cfg = oracle.default_config()
+    st = np.zeros(1, dtype=oracle.LAYER_STATE)
+    buf = np.zeros(32, dtype=np.float32)
+    rc = L.s2o_process_layer_buf_simd(cfg.ctypes.data, st.ctypes.data, 440.0, 48000, 0xFFFFFFF0, NONE, buf.ctypes.data, 32)
+    assert rc == -1   # the reference panics: process.rs:36
+
+
+# ---- Synth (synth.rs) ---------------------------------------------------------------------
+
+def test_synth_voice_allocation_and_stealing():
+    s = oracle.OracleSynth()
+    buf = np.zeros(16, dtype=np.float32)
+    for i in range(8):
+        s.note_on(40 + i)
+        s.sample(buf, 48000)           # voice i is now (8 - i) * 16 frames old at the end
+    used = [s.voice_info(k) for k in range(8)]
+    assert [u[1] for u in used] == list(range(40, 48))      # free slots were taken in index order
+    s.note_on(99)                      # all busy: steal the oldest = slot 0
+    assert s.voice_info(0)[1] == 99 and s.voice_info(0)[2] == 0
+    s.note_off(41)
+    assert s.voice_info(1)[3] == s.voice_info(1)[2]         # release = current offset
+    # a second note_off for the same note finds no active voice: nothing changes (synth.rs:73)
+    before = s.voice_info(1)
+    assert s.note_off(41) is False
+    assert s.voice_info(1)[:4] == before[:4]
+
+
+def test_synth_silence_and_overwrite():
+    s = oracle.OracleSynth()
+    buf = np.full(40, 7.0, dtype=np.float32)
+    s.sample(buf, 48000)
+    assert np.all(buf == 0.0)          # overwritten, not accumulated (synth.rs:201-202)
+
+
+def test_synth_mix_is_sum_in_voice_order():
+    s = oracle.OracleSynth()
+    s.note_on(60); s.note_on(64); s.note_on(67)
+    buf = np.zeros(64, dtype=np.float32)
+    s.sample(buf, 48000)
+    cfg = oracle.default_config()
+    acc = np.zeros(64, dtype=np.float32)
+    for note in (60, 64, 67):
+        st = np.zeros(1, dtype=oracle.LAYER_STATE)
+        one = np.zeros(64, dtype=np.float32)
+        L.s2o_process_layer_buf_simd(cfg.ctypes.data, st.ctypes.data, L.s2o_note_to_pitch(note), 48000, 0, NONE,
+                                     one.ctypes.data, 64)
+        acc = acc + one
+    assert buf.tobytes() == acc.tobytes()
+
+
+def test_bank_render_equals_per_voice_calls_and_carries_state():
+    from synth2_b200 import bankgen
+    b = bankgen.make_bank(5, 400, kinds=(0, 1, 2, 3))
+    st = oracle.bank_init_states(b)
+    a1, bus1 = oracle.bank_render(b, st, 48000, 0, 144)
+    a2, bus2 = oracle.bank_render(b, st, 48000, 0, 256)
+    st_once = oracle.bank_init_states(b)
+    whole, bus = oracle.bank_render(b, st_once, 48000, 0, 400)
+    assert np.concatenate([a1, a2], axis=1).tobytes() == whole.tobytes()   # 144 and 400 are multiples of 16
+    assert np.concatenate([bus1, bus2]).tobytes() == bus.tobytes()
+    assert st.tobytes() == st_once.tobytes()
+    assert np.all(st["frame_offset"] == 400)
+    # multi-threaded baseline mode renders the same voices
+    st_mt = oracle.bank_init_states(b)
+    mt, _ = oracle.bank_render(b, st_mt, 48000, 0, 400, nthreads=3)
+    assert mt.tobytes() == whole.tobytes()
