@@ -103,6 +103,11 @@ int s2_bank_set_voice(s2_bank* bank, size_t index, const s2_voice_desc* voice);
 /* note_off for slot `index` (synth.rs:72-80): release_frame_offset = current_frame_offset. */
 int s2_bank_release_voice(s2_bank* bank, size_t index);
 
+/* Bulk note_off table: release_frame_offset of every voice (S2_NO_RELEASE = still held), one
+   H2D copy of n_voices u32 from `h_release` (pinned memory makes it asynchronous).  This is the
+   per-buffer event upload of a streaming caller (main.rs:138-147 applies MIDI, then samples). */
+int s2_bank_set_releases(s2_bank* bank, const uint32_t* h_release);
+
 /*
  * Render `frames` frames of every active voice, process_layer_buf_simd semantics per voice
  * (x16 blocks, then `frames % 16` scalar-path tail frames), and advance the carried state.

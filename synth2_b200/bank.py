@@ -66,6 +66,10 @@ class VoiceBank:
     def release_voice(self, index: int):
         check(lib().s2_bank_release_voice(self._h, int(index)))
 
+    def set_releases(self, release_offsets):
+        """Bulk note_off table: u32 per voice (NO_RELEASE = held); numpy array or pinned torch tensor."""
+        check(lib().s2_bank_set_releases(self._h, ptr(release_offsets)))
+
     # -- rendering (device buffers: anything with .data_ptr(), or a raw address)
     def render(self, frames: int, voice_out=None, row_stride: int = 0, bus_out=None):
         if voice_out is not None and not row_stride:

@@ -33,12 +33,20 @@ def pitch_table() -> np.ndarray:
     return np.array([note_to_pitch(n) for n in range(128)], dtype=np.float32)
 
 
+# mod-env -> cutoff amounts (octaves at full envelope).  The one-pole filter takes any cutoff
+# (k = exp(-2*pi*f/sr) just underflows towards 0), so its banks use the reference default of 10
+# (synth.rs:150).  The 2nd-order low-pass (dsp_filters.rs:99-109) is only stable below Nyquist:
+# 8000 Hz * 2^1.5 = 22.6 kHz < 24 kHz, so biquad banks sweep 1.5 octaves.
+MOD_TO_LPF_ONE_POLE = (0.0, 10.0)
+MOD_TO_LPF_BIQUAD = (0.0, 1.5)
+
+
 def make_bank(n_voices: int, render_frames: int, first_voice: int = 0, kinds=(OSC_SAW, OSC_SQUARE),
-              mod_to_lpf_choices=(0.0, 10.0), pitches: np.ndarray = None) -> np.ndarray:
+              mod_to_lpf_choices=MOD_TO_LPF_ONE_POLE, pitches: np.ndarray = None) -> np.ndarray:
     """Voices [first_voice, first_voice + n_voices) of the synthetic bank.
 
     note in [24, 108]; cutoff log-uniform [100, 8000] Hz; damping uniform [0.2, 1.414]; A, D, R
-    uniform [5, 500] ms; S uniform [0.2, 0.9]; mod env 0/200/0/0 ms; mod->lpf in {0, 10}; mod->osc 0;
+    uniform [5, 500] ms; S uniform [0.2, 0.9]; mod env 0/200/0/0 ms; mod->lpf drawn from `mod_to_lpf_choices`; mod->osc 0;
     osc gain 1, noise amount 0, noise seed = voice index; oscillator kind cycles through `kinds`
     by voice index; note-on at frame 0; release at 75 % of `render_frames`, rounded down to a
     multiple of 16.

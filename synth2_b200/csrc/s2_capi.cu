@@ -333,6 +333,14 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
     return S2_OK;
 }
 
+int s2_bank_set_releases(s2_bank* b, const uint32_t* h_release) {
+    if (!b || !h_release) return fail(S2_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad, h_release,
+                             b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    return S2_OK;
+}
+
 int s2_bank_render(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out) {
     return bank_render_impl(b, frames, d_voice_out, row_stride, d_bus_out, s2::TRACE_NONE);
 }

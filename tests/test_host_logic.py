@@ -1,0 +1,223 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports exactly what
+include/s2_cuda.h declares, struct layouts agree across header / ctypes / oracle, the host helpers
+match the oracle, and the library refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import synth2_b200 as s2
+from synth2_b200 import _lib, bankgen
+from synth2_b200.shard import voice_range
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "s2_cuda.h").read_text()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 20
+    handle = C.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in s2_cuda.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
+
+
+def test_abi_version_and_error_string():
+    assert s2.lib().s2_abi_version() == 1
+    assert isinstance(s2.lib().s2_last_error(), bytes)
+
+
+def _c_struct_fields(name):
+    m = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", HEADER, re.S)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, rest = decl.split(None, 1)
+        for f in rest.split(","):
+            fields.append((f.strip(), ctype))
+    return fields
+
+
+@pytest.mark.parametrize("cname,dtype", [("s2_voice_desc", s2.VOICE_DESC), ("s2_voice_state", s2.VOICE_STATE)])
+def test_struct_layout_matches_header(cname, dtype):
+    fields = _c_struct_fields(cname)
+    assert [f for f, _ in fields] == list(dtype.names)
+    for (f, ctype), n in zip(fields, dtype.names):
+        want = {"uint32_t": "<u4", "float": "<f4"}[ctype]
+        assert dtype[n].str == want, f
+    assert dtype.itemsize == 4 * len(fields)
+
+
+def test_oracle_voice_desc_has_the_same_layout():
+    src = (ROOT / "oracle" / "s2_oracle.h").read_text()
+    m = re.search(r"typedef struct \{([^}]*)\} s2o_voice_desc;", src, re.S)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [f.strip() for f in decl.split(None, 1)[1].split(",")]
+    assert names == list(s2.VOICE_DESC.names)
+    m = re.search(r"typedef struct \{([^}]*)\} s2o_voice_state;", src, re.S)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [f.strip() for f in decl.split(None, 1)[1].split(",")]
+    assert names == list(s2.VOICE_STATE.names)
+
+
+def test_note_to_pitch_matches_oracle_for_all_notes():
+    for n in range(128):
+        a = np.float32(s2.note_to_pitch(n))
+        b = np.float32(oracle.lib().s2o_note_to_pitch(n))
+        assert a.tobytes() == b.tobytes()
+    assert s2.note_to_pitch(69) == 440.0
+
+
+def test_default_voice_is_the_reference_default_patch():
+    d = s2.default_voice(1)[0]
+    cfg = oracle.default_config()[0]
+    assert d["osc_kind"] == cfg["osc_kind"] == s2.OSC_SAW
+    assert d["osc_gain"] == cfg["osc_gain"] == 1.0
+    assert d["noise_amt"] == cfg["noise"] == 0.0
+    assert d["lpf_freq_hz"] == cfg["lpf_freq"] == 200.0
+    assert (d["amp_attack_ms"], d["amp_decay_ms"], d["amp_sustain"], d["amp_release_ms"]) == (100.0, 100.0, 0.5, 100.0)
+    assert tuple(cfg["amp_env"]) == (100.0, 100.0, 0.5, 100.0)
+    assert (d["mod_attack_ms"], d["mod_decay_ms"], d["mod_sustain"], d["mod_release_ms"]) == (0.0, 200.0, 0.0, 0.0)
+    assert tuple(cfg["mod_env"]) == (0.0, 200.0, 0.0, 0.0)
+    assert d["mod_env_to_osc_freq"] == cfg["mod_env_to_osc_freq"] == 0.0
+    assert d["mod_env_to_lpf_freq"] == cfg["mod_env_to_lpf_freq"] == 10.0
+    assert d["release_offset"] == s2.NO_RELEASE and d["active"] == 0
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry must fail loudly; with one, this test is a no-op."""
+    n = C.c_int(0)
+    rc = s2.lib().s2_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(s2.S2Error) as e:
+        s2.VoiceBank(bankgen.make_bank(4, 64), 48000, 0)
+    assert e.value.code == _lib.S2_ERR_NO_DEVICE
+    with pytest.raises(s2.S2Error):
+        s2.Synth()
+
+
+def test_argument_validation_happens_before_the_device():
+    h = C.c_void_p()
+    v = bankgen.make_bank(2, 64)
+    rc = s2.lib().s2_bank_create(0, 48000, 0, 0, _lib.ptr(v), None, C.byref(h))
+    assert rc == _lib.S2_ERR_INVALID
+    rc = s2.lib().s2_bank_create(0, 0, 0, 2, _lib.ptr(v), None, C.byref(h))
+    assert rc == _lib.S2_ERR_INVALID
+    rc = s2.lib().s2_bank_create(0, 48000, 5, 2, _lib.ptr(v), None, C.byref(h))
+    assert rc == _lib.S2_ERR_INVALID
+    assert b"filter_kind" in s2.lib().s2_last_error()
+    assert s2.lib().s2_bank_render(None, 16, None, 0, None) == _lib.S2_ERR_INVALID
+    assert s2.lib().s2_synth_note_on(None, 60, 1.0) == _lib.S2_ERR_INVALID
+
+
+def test_product_code_never_touches_the_oracle():
+    for p in list((ROOT / "synth2_b200").rglob("*.py")) + list((ROOT / "synth2_b200" / "csrc").glob("*.cu")) \
+            + list((ROOT / "synth2_b200" / "csrc").glob("*.h")):
+        text = p.read_text()
+        assert "s2o_" not in text and "libs2oracle" not in text and "import oracle" not in text, p
+
+
+# ---- synthetic bank generator --------------------------------------------------------------
+
+def test_bankgen_is_counter_based():
+    whole = bankgen.make_bank(100, 48000)
+    part = bankgen.make_bank(40, 48000, first_voice=60)
+    assert whole[60:].tobytes() == part.tobytes()
+    assert whole["release_offset"][0] == 36000 and 36000 % 16 == 0
+    assert np.all((whole["lpf_freq_hz"] >= 100) & (whole["lpf_freq_hz"] <= 8000))
+    assert np.all((whole["damping"] >= 0.2) & (whole["damping"] <= 1.4141))
+    assert set(np.unique(whole["mod_env_to_lpf_freq"])) <= {0.0, 10.0}
+    assert np.all(whole["noise_seed"] == np.arange(100))
+    assert list(whole["osc_kind"][:4]) == [s2.OSC_SAW, s2.OSC_SQUARE, s2.OSC_SAW, s2.OSC_SQUARE]
+
+
+def test_splitmix64_known_answer():
+    # splitmix64 reference stream for seed 0: first output
+    assert int(bankgen.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+
+
+# ---- sharding --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_voice_ranges_partition(world):
+    n = 262144 + 5
+    spans = [voice_range(r, world, n) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for a, b in zip(spans[:-1], spans[1:]):
+        assert a[1] == b[0]
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _shard_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from synth2_b200.shard import reduce_master_bus
+    V, T = 48, 512
+    lo, hi = voice_range(rank, world, V)
+    mine = bankgen.make_bank(hi - lo, 4 * T, first_voice=lo, kinds=(0, 1, 2, 3))
+    st = oracle.bank_init_states(mine)
+    _, bus = oracle.bank_render(mine, st, 48000, 0, T)         # CPU stand-in for the per-GPU render
+    t = torch.from_numpy(bus.copy())
+    reduce_master_bus(t, dst=0)
+    if rank == 0:
+        q.put(t.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_master_bus_world2_gloo():
+    """N>1 path on CPU: each rank renders its voice range, one reduce sums the buses on rank 0."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    V, T = 48, 512
+    full = bankgen.make_bank(V, 4 * T, kinds=(0, 1, 2, 3))
+    st = oracle.bank_init_states(full)
+    _, want = oracle.bank_render(full, st, 48000, 0, T)
+    np.testing.assert_allclose(got, want, atol=1e-4 * max(1.0, float(np.max(np.abs(want)))), rtol=0)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
