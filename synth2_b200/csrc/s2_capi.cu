@@ -10,6 +10,7 @@
 #include "../../include/s2_cuda.h"
 #include "s2_internal.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -61,8 +62,9 @@ int validate_voice(const s2_voice_desc& d, size_t index) {
 uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float ubits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-void pack_voice(const s2_voice_desc& d, float* col, size_t pitch) {
+void pack_voice(const s2_voice_desc& d, uint32_t row, float* col, size_t pitch) {
     using namespace s2;
+    col[P_ROW * pitch] = ubits(row);
     col[P_KIND * pitch] = ubits(d.osc_kind);
     col[P_SEED * pitch] = ubits(d.noise_seed);
     col[P_PITCH * pitch] = d.pitch_hz;
@@ -118,7 +120,15 @@ struct s2_bank {
     size_t partials_cap = 0;     // floats
     float* d_bus = nullptr;
     size_t bus_cap = 0;          // floats
-    std::vector<VoiceBook> book;
+    std::vector<VoiceBook> book;  // indexed by voice
+    // "Slots": device arrays are indexed by slot, not by the caller's voice index.  Banks wider than
+    // one warp are sorted by (active, oscillator kind) at creation so that the 32 lanes of a warp run
+    // the same oscillator code (kind-uniform warps take the straight-line specialised loop); output
+    // rows, state get/set and per-voice calls keep the caller's indices.  Banks of <= 32 voices keep
+    // the identity order, which also keeps the bus sum in the reference's voice order.
+    std::vector<uint32_t> slot_of_voice, voice_of_slot;
+    bool identity = true;
+    uint32_t* d_stage = nullptr;  // staging for the bulk note-off table when slots are permuted
     uint64_t total_frames = 0;
     uint64_t max_offset = 0;     // upper bound of any active voice's frame offset
     size_t n_sine = 0;
@@ -259,13 +269,27 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->vpad = (n_voices + 31) & ~(size_t)31;
     b->book.resize(n_voices);
 
+    b->voice_of_slot.resize(n_voices);
+    b->slot_of_voice.resize(n_voices);
+    for (size_t i = 0; i < n_voices; i++) b->voice_of_slot[i] = (uint32_t)i;
+    if (n_voices > 32) {
+        auto key = [&](uint32_t v) { return voices[v].active ? voices[v].osc_kind : 4u; };
+        std::stable_sort(b->voice_of_slot.begin(), b->voice_of_slot.end(),
+                         [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+    }
+    for (size_t s = 0; s < n_voices; s++) {
+        b->slot_of_voice[b->voice_of_slot[s]] = (uint32_t)s;
+        if (b->voice_of_slot[s] != s) b->identity = false;
+    }
+
     std::vector<float> hp((size_t)s2::P_COUNT * b->vpad, 0.0f), hs((size_t)s2::S_COUNT * b->vpad, 0.0f);
     for (size_t i = 0; i < n_voices; i++) {
-        pack_voice(voices[i], hp.data() + i, b->vpad);
+        const size_t slot = b->slot_of_voice[i];
+        pack_voice(voices[i], (uint32_t)i, hp.data() + slot, b->vpad);
         s2_voice_state st;
         memset(&st, 0, sizeof st);
         st.frame_offset = voices[i].frame_offset;
-        pack_state(st, hs.data() + i, b->vpad);
+        pack_state(st, hs.data() + slot, b->vpad);
         b->book[i] = {voices[i].frame_offset, 0, voices[i].active ? 1u : 0u, voices[i].osc_kind};
         if (voices[i].active && voices[i].frame_offset > b->max_offset) b->max_offset = voices[i].frame_offset;
         if (voices[i].osc_kind == S2_OSC_SINE) b->n_sine++;
@@ -292,6 +316,7 @@ void s2_bank_destroy(s2_bank* b) {
     cudaFree(b->d_state);
     cudaFree(b->d_partials);
     cudaFree(b->d_bus);
+    cudaFree(b->d_stage);
     delete b;
 }
 
@@ -304,15 +329,16 @@ int s2_bank_set_voice(s2_bank* b, size_t index, const s2_voice_desc* voice) {
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(b->device));
     float hp[s2::P_COUNT], hs[s2::S_COUNT];
-    pack_voice(*voice, hp, 1);
+    const size_t slot = b->slot_of_voice[index];   // the voice keeps its slot (a changed kind makes that warp mixed)
+    pack_voice(*voice, (uint32_t)index, hp, 1);
     s2_voice_state st;
     memset(&st, 0, sizeof st);            // st::Layer::default(), synth.rs:68
     st.frame_offset = voice->frame_offset;
     pack_state(st, hs, 1);
     // one 4-byte element per SoA row
-    CUDA_TRY(cudaMemcpy2DAsync(b->d_params + index, b->vpad * sizeof(float), hp, sizeof(float), sizeof(float),
+    CUDA_TRY(cudaMemcpy2DAsync(b->d_params + slot, b->vpad * sizeof(float), hp, sizeof(float), sizeof(float),
                                s2::P_COUNT, cudaMemcpyHostToDevice, b->stream));
-    CUDA_TRY(cudaMemcpy2DAsync(b->d_state + index, b->vpad * sizeof(float), hs, sizeof(float), sizeof(float),
+    CUDA_TRY(cudaMemcpy2DAsync(b->d_state + slot, b->vpad * sizeof(float), hs, sizeof(float), sizeof(float),
                                s2::S_COUNT, cudaMemcpyHostToDevice, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));   // hp/hs live on this stack frame
     if (b->book[index].osc_kind == S2_OSC_SINE) b->n_sine--;
@@ -327,8 +353,8 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
     if (index >= b->n_voices) return fail(S2_ERR_INVALID, "voice index %zu out of range", index);
     CUDA_TRY(cudaSetDevice(b->device));
     const uint32_t rel = current_offset(b, index);   // release_frame_offset = current_frame_offset (synth.rs:75)
-    CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad + index, &rel, sizeof rel,
-                             cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad + b->slot_of_voice[index], &rel,
+                             sizeof rel, cudaMemcpyHostToDevice, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return S2_OK;
 }
@@ -336,8 +362,16 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
 int s2_bank_set_releases(s2_bank* b, const uint32_t* h_release) {
     if (!b || !h_release) return fail(S2_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->device));
-    CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad, h_release,
-                             b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    uint32_t* row = reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad);
+    if (b->identity) {
+        CUDA_TRY(cudaMemcpyAsync(row, h_release, b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+        return S2_OK;
+    }
+    if (!b->d_stage) CUDA_TRY(cudaMalloc(&b->d_stage, b->n_voices * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpyAsync(b->d_stage, h_release, b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(s2::launch_gather_u32(b->d_stage, b->d_params + (size_t)s2::P_ROW * b->vpad, row,
+                                   (uint32_t)b->n_voices, b->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return S2_OK;
 }
 
@@ -374,8 +408,9 @@ int s2_bank_get_state(s2_bank* b, s2_voice_state* out) {
     CUDA_TRY(cudaMemcpyAsync(hs.data(), b->d_state, hs.size() * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     const size_t p = b->vpad;
-    for (size_t i = 0; i < b->n_voices; i++) {
-        s2_voice_state& s = out[i];
+    for (size_t v = 0; v < b->n_voices; v++) {
+        const size_t i = b->slot_of_voice[v];
+        s2_voice_state& s = out[v];
         s.phase = hs[s2::S_PHASE * p + i];
         s.has_phase = fbits(hs[s2::S_HAS_PHASE * p + i]);
         s.frame_offset = fbits(hs[s2::S_OFFSET * p + i]);
@@ -394,7 +429,7 @@ int s2_bank_set_state(s2_bank* b, const s2_voice_state* in) {
     std::vector<float> hs((size_t)s2::S_COUNT * b->vpad, 0.0f);
     uint64_t mx = 0;
     for (size_t i = 0; i < b->n_voices; i++) {
-        pack_state(in[i], hs.data() + i, b->vpad);
+        pack_state(in[i], hs.data() + b->slot_of_voice[i], b->vpad);
         b->book[i].start_offset = in[i].frame_offset;
         b->book[i].start_total = b->total_frames;
         if (b->book[i].active && in[i].frame_offset > mx) mx = in[i].frame_offset;

@@ -16,6 +16,7 @@ enum ParamIdx {
     P_MA, P_MD, P_MS, P_MR,   // mod ADSR
     P_AMT_OSC, P_AMT_LPF,
     P_RELEASE, P_ACTIVE,
+    P_ROW,                    // caller-visible voice index of this slot (output row, see s2_capi.cu "slots")
     P_COUNT
 };
 
@@ -45,6 +46,8 @@ constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, c
 cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream);
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* bus,
                               cudaStream_t stream);
-cudaError_t upload_sin_table();     // copies the table into __device__ memory of the current device
+// release_row[slot] = staged[voice_of_slot[slot]]  (bulk note-off table given in voice order)
+cudaError_t launch_gather_u32(const uint32_t* staged, const float* row_index_bits, uint32_t* dst_row,
+                              uint32_t n, cudaStream_t stream);
 
 }  // namespace s2

@@ -251,7 +251,9 @@ __device__ __forceinline__ void chunk_fast(const Lane& L, const OscC& o, const F
                                            const float* sintab) {
     uint32_t n = n0;
     float xf = __uint2float_rn(n0);               // exact: the caller guarantees n0 + 32 <= 2^24
-#pragma unroll
+    // 8 frames per trip: long enough for the scheduler to overlap the two recurrences (phase, filter)
+    // of neighbouring frames, short enough (~3 KB of SASS) to live in the instruction cache.
+#pragma unroll 2
     for (int j = 0; j < kChunk / 4; j++) {
         float o4[4];
 #pragma unroll
@@ -373,6 +375,16 @@ render_seq_kernel(const RenderArgs a) {
     float* myrow = tile + lane * kTileStride;
     const size_t stride = a.row_stride;
     float* __restrict__ gout = a.voice_out;
+    // Output rows are indexed by the caller's voice index, which the bank may have permuted into
+    // kind-uniform warps (P_ROW).  Lane (q, c4) writes 16 bytes of rows 4*i + q, i = 0..7.
+    const uint32_t my_out_row = exists ? __float_as_uint(P[P_ROW * vp]) : 0xffffffffu;
+    const int q = lane >> 3, c4 = (lane & 7) * 4;
+    float* rowp[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t r = __shfl_sync(0xffffffffu, my_out_row, 4 * i + q);
+        rowp[i] = (gout && r != 0xffffffffu) ? gout + (size_t)r * stride + c4 : nullptr;
+    }
     float* __restrict__ gbus = a.bus_partials ? a.bus_partials + (size_t)gwarp * frames : nullptr;
 
     for (uint32_t t0 = 0; t0 < frames; t0 += kChunk) {
@@ -437,19 +449,19 @@ render_seq_kernel(const RenderArgs a) {
         if (gout) {
             if (cnt == kChunk) {
                 // transposed write-back: lanes 8q..8q+7 cover 128 contiguous bytes of row 4*i + q
-                const int q = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const uint32_t r = 4 * i + q;
-                    if (vbase + r < a.n_voices) {
-                        const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
-                        __stcs(reinterpret_cast<float4*>(gout + (size_t)(vbase + r) * stride + t0 + c4), val);
+                    if (rowp[i]) {
+                        const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                        __stcs(reinterpret_cast<float4*>(rowp[i] + t0), val);
                     }
                 }
             } else {
-                for (uint32_t r = 0; r < 32u && vbase + r < a.n_voices; r++)
+                for (uint32_t r = 0; r < 32u && vbase + r < a.n_voices; r++) {
+                    const uint32_t orow = __shfl_sync(0xffffffffu, my_out_row, r);
                     if ((uint32_t)lane < cnt)
-                        gout[(size_t)(vbase + r) * stride + t0 + lane] = tile[r * kTileStride + lane];
+                        gout[(size_t)orow * stride + t0 + lane] = tile[r * kTileStride + lane];
+                }
             }
         }
         if (gbus) {
@@ -483,6 +495,19 @@ __global__ void bus_reduce_kernel(const float* __restrict__ partials, uint32_t n
     float acc = n_warps ? partials[t] : 0.0f;     // 0.0 + p_0 == p_0 (p_0 is never -0.0: it starts from +0.0)
     for (uint32_t w = 1; w < n_warps; w++) acc = __fadd_rn(acc, partials[(size_t)w * frames + t]);
     bus[t] = acc;
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ staged, const float* __restrict__ row_index_bits,
+                                  uint32_t* __restrict__ dst, uint32_t n) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = staged[__float_as_uint(row_index_bits[s])];
+}
+
+cudaError_t launch_gather_u32(const uint32_t* staged, const float* row_index_bits, uint32_t* dst_row,
+                              uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    gather_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(staged, row_index_bits, dst_row, n);
+    return cudaGetLastError();
 }
 
 template <int FILTER, int TRACE>
