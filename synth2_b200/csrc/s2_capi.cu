@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -96,6 +97,10 @@ void pack_state(const s2_voice_state& s, float* col, size_t pitch) {
     col[S_X2 * pitch] = s.x2;
     col[S_Y1 * pitch] = s.y1;
     col[S_Y2 * pitch] = s.y2;
+    // derived-constant memo: empty (the kernel re-derives and refills it)
+    for (int k = S_FO_KEY; k < S_COUNT; k++) col[k * pitch] = 0.0f;
+    col[S_FO_KEY * pitch] = ubits(kNoKey);
+    col[S_FL_KEY * pitch] = ubits(kNoKey);
 }
 
 struct VoiceBook {           // host mirror of what the device will hold, O(1) per render
@@ -128,6 +133,7 @@ struct s2_bank {
     // the identity order, which also keeps the bus sum in the reference's voice order.
     std::vector<uint32_t> slot_of_voice, voice_of_slot;
     bool identity = true;
+    int nv = 1;                   // voices per lane: 2 (packed f32x2 arithmetic) for banks wider than a warp
     uint32_t* d_stage = nullptr;  // staging for the bulk note-off table when slots are permuted
     uint64_t total_frames = 0;
     uint64_t max_offset = 0;     // upper bound of any active voice's frame offset
@@ -156,7 +162,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
         return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
     CUDA_TRY(cudaSetDevice(b->device));
 
-    const uint32_t n_warps = (uint32_t)((b->n_voices + 31) / 32);
+    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
     float* partials = nullptr;
     if (d_bus_out) {
         if (n_warps == 1) {
@@ -184,7 +190,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     a.row_stride = row_stride;
     a.bus_partials = partials;
     a.has_sine = b->n_sine ? 1u : 0u;
-    CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->stream));
+    CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
         CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, d_bus_out, b->stream));
@@ -266,8 +272,13 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->sample_rate = sample_rate;
     b->filter_kind = filter_kind;
     b->n_voices = n_voices;
-    b->vpad = (n_voices + 31) & ~(size_t)31;
+    b->vpad = (n_voices + 63) & ~(size_t)63;
     b->book.resize(n_voices);
+    b->nv = 1;   // 2 = two voices per lane with packed f32x2 math: fewer issue slots but half the warps; measured no faster
+    if (const char* f = getenv("S2_FORCE_NV")) {          // test hook: exercise either lane width on any bank
+        if (f[0] == '1') b->nv = 1;
+        if (f[0] == '2') b->nv = 2;
+    }
 
     b->voice_of_slot.resize(n_voices);
     b->slot_of_voice.resize(n_voices);

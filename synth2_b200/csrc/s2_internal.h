@@ -21,7 +21,16 @@ enum ParamIdx {
 };
 
 // Carried state, same layout: state[k * vpad + v].
-enum StateIdx { S_PHASE = 0, S_HAS_PHASE, S_OFFSET, S_LAST, S_X1, S_X2, S_Y1, S_Y2, S_COUNT };
+enum StateIdx {
+    S_PHASE = 0, S_HAS_PHASE, S_OFFSET, S_LAST, S_X1, S_X2, S_Y1, S_Y2,
+    // Memo of the constants derived from the oscillator frequency and the filter cutoff (divisions,
+    // exp / sin / cos in binary64), keyed by the exact input bits: a launch that finds its key reuses
+    // them instead of re-deriving ~1000 instructions per voice.  Not part of s2_voice_state.
+    S_FO_KEY, S_OSC_P, S_OSC_D, S_OSC_SLOPE, S_OSC_HALF, S_OSC_TS1, S_OSC_TS2,
+    S_FL_KEY, S_DAMP_KEY, S_FC_C0, S_FC_C1, S_FC_C2,
+    S_COUNT
+};
+constexpr uint32_t kNoKey = 0x7fc00001u;   // a NaN payload no frequency can have
 
 enum TraceMode { TRACE_NONE = 0, TRACE_PHASE = 1 };
 
@@ -43,7 +52,9 @@ constexpr int kChunk = 32;          // frames per warp tile
 constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, conflict-free STS.128/LDS.128
 
 // Launchers (s2_kernels.cu).  Return the cudaError_t of the launch.
-cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream);
+// nv = voices per lane: 1 (scalar FP32) or 2 (packed f32x2); a warp renders 32*nv consecutive slots.
+cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, int nv, cudaStream_t stream);
+uint32_t render_warps(uint32_t n_voices, int nv);
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* bus,
                               cudaStream_t stream);
 // release_row[slot] = staged[voice_of_slot[slot]]  (bulk note-off table given in voice order)
