@@ -150,8 +150,8 @@ def cpu_baseline(args, bankgen):
     probe = bankgen.make_bank(max(cores * 4, 32), RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     rate, _ = cpu_port_throughput(probe, cores, 2048)
     want = max(rate * args.cpu_seconds, 1.0)
-    frames = BLOCK * 4
-    nv = int(min(max(want / frames, cores), 8192))
+    nv = max(cores * 32, 256)
+    frames = int(min(max(want / nv // BLOCK, 1), 64)) * BLOCK
     sample = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     rate, dt = cpu_port_throughput(sample, cores, frames)
     return {"value": rate, "unit": "voice-samples/s", "cores": cores, "kind": "port",
@@ -305,12 +305,12 @@ def main():
     kernel_ms = ms / len(frames)            # one render kernel per step is the whole timed region
     achieved = V * total_frames * BYTES_PER_VOICE_SAMPLE / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "s2::render_seq_kernel<1,0>", "peak_source": peak_src,
+                "traffic": None, "kernel": "s2::render_kernel<1,1,0> (NV=1 voice/lane, FILTER=biquad)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": kernel_ms}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
-            roofline["traffic"] = json.loads(prof.read_text()).get("render_seq_kernel_bytes_per_launch")
+            roofline["traffic"] = json.loads(prof.read_text()).get("render_kernel_bytes_per_launch")
         except Exception:
             pass
 
