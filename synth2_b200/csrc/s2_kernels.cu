@@ -272,12 +272,40 @@ template <int NV> __device__ __forceinline__ vf<NV> vsplat(float x);
 template <> __device__ __forceinline__ float vsplat<1>(float x) { return x; }
 template <> __device__ __forceinline__ float2 vsplat<2>(float x) { return make_float2(x, x); }
 
+// CONTRACTION HAZARD (ptxas 12.9, sm_100a): a packed multiply whose result feeds a packed add is fused
+// into FFMA2 — with the __fmul2_rn/__fadd2_rn builtins AND with explicit `mul.rn.f32x2` / `add.rn.f32x2`
+// PTX, -fmad=false notwithstanding (tools/ubench/fuse_check.cu; scalar __fmul_rn + __fadd_rn is not
+// fused).  That moves results by an ulp and can flip a square wave's sign.  Rule used in this file: the
+// result of pmul2 never feeds padd2; where the reference adds to a product, the add is done with scalar
+// __fadd_rn per element (vadd(float2, float2) below always is).
+__device__ __forceinline__ float2 padd2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 pmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 pfma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 __device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return pmul2(a, b); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return pfma2(a, b, c); }
 
 // Per-lane constants and state of the fast path, NV voices wide.
 template <int NV> struct FastV {
@@ -465,7 +493,7 @@ template <int FILTER, int KIND, bool GCONST, bool NAMT0, bool ALIGNED8, int TRAC
 __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restrict__ amp, uint32_t kind, uint32_t rot,
                                               uint32_t n0, float* __restrict__ row, const float* sintab) {
     const float2 one2 = make_float2(1.0f, 1.0f), none2 = make_float2(-1.0f, -1.0f), two2 = make_float2(2.0f, 2.0f);
-    const float2 P2 = make_float2(F.P, F.P), slope2 = make_float2(F.slope, F.slope), nhalf2 = make_float2(F.nhalf, F.nhalf);
+    const float2 P2 = make_float2(F.P, F.P), slope2 = make_float2(F.slope, F.slope);
     const float2 ts1_2 = make_float2(F.ts1, F.ts1), ts2_2 = make_float2(F.ts2, F.ts2);
     const float2 gain2 = make_float2(F.gain, F.gain), namt2 = make_float2(F.namt, F.namt);
     const float2 ey0_2 = make_float2(F.ey0, F.ey0);
@@ -495,18 +523,19 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             ph = tb >= 1.0f ? __fadd_rn(tb, -1.0f) : tb;
             const float2 ph2 = make_float2(pa, pb);
             // ---- waveform: x = period.mul_add(phase, 0); `% period` is a no-op
-            const float2 x2 = __fmul2_rn(P2, ph2);
+            const float2 x2 = pmul2(P2, ph2);
             float2 osc2;
             if (KIND == 1) {
-                osc2 = __ffma2_rn(slope2, x2, one2);
+                osc2 = pfma2(slope2, x2, one2);
             } else if (KIND == 0) {
-                const float2 dl = __fadd2_rn(x2, nhalf2);
+                // scalar adds: x2 is a packed product (contraction hazard above)
+                const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
                 osc2.x = __uint_as_float((__float_as_uint(dl.x) & 0x80000000u) ^ 0xbf800000u);
                 osc2.y = __uint_as_float((__float_as_uint(dl.y) & 0x80000000u) ^ 0xbf800000u);
             } else if (KIND == 2) {
-                const float2 dl = __fadd2_rn(x2, nhalf2);
-                const float2 a = __ffma2_rn(ts1_2, x2, one2);
-                const float2 b = __ffma2_rn(ts2_2, dl, none2);
+                const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
+                const float2 a = pfma2(ts1_2, x2, one2);
+                const float2 b = pfma2(ts2_2, dl, none2);
                 osc2.x = dl.x < 0.0f ? a.x : b.x;
                 osc2.y = dl.y < 0.0f ? a.y : b.y;
             } else {
@@ -537,11 +566,11 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             const uint32_t ha = (ALIGNED8 ? (nb ^ fi) : (rot ^ (n + fi))) * 0x9e3779b9u;
             const uint32_t hb = (ALIGNED8 ? (nb ^ (fi + 1u)) : (rot ^ (n + fi + 1u))) * 0x9e3779b9u;
             const float2 v2 = make_float2(__uint2float_rn(ha & 0xffffu), __uint2float_rn(hb & 0xffffu));
-            const float2 q2 = __ffma2_rn(v2, make_float2(0x1.0001p-16f, 0x1.0001p-16f),
-                                         __fmul2_rn(v2, make_float2(0x1.0001p-48f, 0x1.0001p-48f)));
-            const float2 nz2 = __ffma2_rn(q2, two2, none2);
+            const float2 q2 = pfma2(v2, make_float2(0x1.0001p-16f, 0x1.0001p-16f),
+                                         pmul2(v2, make_float2(0x1.0001p-48f, 0x1.0001p-48f)));
+            const float2 nz2 = pfma2(q2, two2, none2);
             // ---- process.rs:341-358 (ADD, x16 quirk); nz + 0.0 == nz bit-for-bit
-            const float2 u2 = __fadd2_rn(__fadd2_rn(osc2, gain2), NAMT0 ? nz2 : __fadd2_rn(nz2, namt2));
+            const float2 u2 = padd2(padd2(osc2, gain2), NAMT0 ? nz2 : padd2(nz2, namt2));
             // ---- filter recurrence, scalar
             const float ya = filt_step<FILTER>(u2.x, fc, fs);
             const float yb = filt_step<FILTER>(u2.y, fc, fs);
@@ -553,7 +582,7 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
                 g2.y = env_x16(A, __fadd_rn(xf, 1.0f));
                 xf = __fadd_rn(xf, 2.0f);
             }
-            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : __fmul2_rn(make_float2(ya, yb), g2);
+            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(make_float2(ya, yb), g2);
             o4[2 * h] = out2.x;
             o4[2 * h + 1] = out2.y;
         }

@@ -371,6 +371,28 @@ def test_split_invariance_bitwise():
         assert sa.tobytes() == sb.tobytes()
 
 
+@pytest.mark.parametrize("filter_kind", [0, 1])
+def test_lane_widths_agree_bitwise(filter_kind, monkeypatch):
+    """NV = 1 (time-packed) and NV = 2 (voice-packed) kernels perform the same IEEE operations per voice:
+    identical bits, including through envelope ramps, modulated segments and the scalar tail."""
+    frames = [4096, 4096, 2048, 1000]
+    v = bank_for(filter_kind, 160, sum(frames), kinds=(0, 1, 2, 3))
+    v["noise_amt"] = (np.arange(160) % 2) * 0.5
+    v["mod_env_to_osc_freq"][::7] = 0.5
+    v["release_offset"] = 6000
+    outs = {}
+    for nv in ("1", "2"):
+        monkeypatch.setenv("S2_FORCE_NV", nv)
+        outs[nv] = gpu_bank_render(v, filter_kind, frames)
+    monkeypatch.delenv("S2_FORCE_NV")
+    a, b = outs["1"], outs["2"]
+    bad = np.argwhere(a[0] != b[0])
+    assert bad.size == 0, f"first differing (voice, frame): {bad[:5].tolist()}"
+    assert a[2].tobytes() == b[2].tobytes()
+    scale = max(1.0, float(np.max(np.abs(a[1]))))
+    assert float(np.max(np.abs(a[1] - b[1]))) <= 1e-5 * scale     # bus: different slot grouping, same voices
+
+
 def test_errors_are_reported_not_crashes():
     v = bankgen.make_bank(4, 64)
     bad = v.copy(); bad["osc_kind"][0] = 9
