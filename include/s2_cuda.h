@@ -126,6 +126,14 @@ int s2_bank_render(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_
 int s2_bank_render_bus_host(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_stride,
                             float* h_bus_out);
 
+/* Streaming form: enqueues the same work (render, mix, device->host copy of the mix into PINNED host
+   memory) and returns without synchronising, so a caller can keep two buffers in flight exactly like
+   the reference's player does (audio_player.rs:56-60, sync_channel(2)): enqueue buffer i+1, then wait
+   for buffer i (an event on the bank's stream, or s2_bank_sync).  `h_pinned_bus_out` must stay valid
+   until then. */
+int s2_bank_render_bus_host_async(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_stride,
+                                  float* h_pinned_bus_out);
+
 /* Checkpoint / restore / test hook.  Host arrays of n_voices entries; synchronises. */
 int s2_bank_get_state(s2_bank* bank, s2_voice_state* out);
 int s2_bank_set_state(s2_bank* bank, const s2_voice_state* in);

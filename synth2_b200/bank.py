@@ -86,6 +86,12 @@ class VoiceBank:
         check(lib().s2_bank_render_bus_host(self._h, int(frames), ptr(voice_out), int(row_stride), ptr(out)))
         return out
 
+    def render_bus_host_async(self, frames: int, pinned_out, voice_out=None, row_stride: int = 0):
+        """Streaming form: enqueue render + mix + D2H of the mix into pinned host memory, no sync."""
+        if voice_out is not None and not row_stride:
+            row_stride = int(voice_out.stride(0)) if hasattr(voice_out, "stride") else int(frames)
+        check(lib().s2_bank_render_bus_host_async(self._h, int(frames), ptr(voice_out), int(row_stride), ptr(pinned_out)))
+
     def trace_phase(self, frames: int, phase_out, row_stride: int = 0):
         if not row_stride:
             row_stride = int(phase_out.stride(0)) if hasattr(phase_out, "stride") else int(frames)

@@ -168,7 +168,8 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
         if (n_warps == 1) {
             partials = d_bus_out;   // a single warp sums its voices in index order: that IS the bus
         } else {
-            const size_t need = (size_t)n_warps * frames;
+            // per-warp partials followed by the stage-1 segment sums of the bus reduction
+            const size_t need = ((size_t)n_warps + s2::bus_segments(n_warps)) * frames;
             if (need > b->partials_cap) {
                 if (b->d_partials) CUDA_TRY(cudaFree(b->d_partials));
                 b->d_partials = nullptr; b->partials_cap = 0;
@@ -193,8 +194,9 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
-        CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, d_bus_out, b->stream));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, partials + (size_t)n_warps * frames,
+                                       d_bus_out, b->stream));
+        g_launches.fetch_add(2, std::memory_order_relaxed);
     }
     b->total_frames += frames;
     b->max_offset += frames;
@@ -396,6 +398,14 @@ int s2_bank_trace_phase(s2_bank* b, size_t frames, float* d_phase_out, size_t ro
 }
 
 int s2_bank_render_bus_host(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* h_bus_out) {
+    int rc = s2_bank_render_bus_host_async(b, frames, d_voice_out, row_stride, h_bus_out);
+    if (rc) return rc;
+    if (frames == 0) return S2_OK;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+int s2_bank_render_bus_host_async(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* h_bus_out) {
     if (!b || !h_bus_out) return fail(S2_ERR_INVALID, "null argument");
     if (frames == 0) return S2_OK;
     CUDA_TRY(cudaSetDevice(b->device));
@@ -408,7 +418,6 @@ int s2_bank_render_bus_host(s2_bank* b, size_t frames, float* d_voice_out, size_
     int rc = bank_render_impl(b, frames, d_voice_out, row_stride, b->d_bus, s2::TRACE_NONE);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h_bus_out, b->d_bus, frames * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    CUDA_TRY(cudaStreamSynchronize(b->stream));
     return S2_OK;
 }
 

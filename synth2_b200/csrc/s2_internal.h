@@ -55,8 +55,10 @@ constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, c
 // nv = voices per lane: 1 (scalar FP32) or 2 (packed f32x2); a warp renders 32*nv consecutive slots.
 cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, int nv, cudaStream_t stream);
 uint32_t render_warps(uint32_t n_voices, int nv);
-cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* bus,
-                              cudaStream_t stream);
+// two kernels; seg_scratch holds bus_segments(n_warps) * frames floats
+cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
+                              float* bus, cudaStream_t stream);
+uint32_t bus_segments(uint32_t n_warps);
 // release_row[slot] = staged[voice_of_slot[slot]]  (bulk note-off table given in voice order)
 cudaError_t launch_gather_u32(const uint32_t* staged, const float* row_index_bits, uint32_t* dst_row,
                               uint32_t n, cudaStream_t stream);

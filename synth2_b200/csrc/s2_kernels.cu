@@ -11,6 +11,7 @@
 // intrinsics so nothing is contracted or reassociated (the file is also built with -fmad=false).
 // Reference line numbers are relative to /root/reference/components/s2_lib/src/.
 #include "s2_internal.h"
+#include "s2_math.h"
 
 // 1: biquad products are fused into the running sum (FFMA); 0: every product and sum rounded
 // separately, as the source reads.  A resonant low-cutoff biquad in f32 direct form amplifies
@@ -122,11 +123,11 @@ __device__ float env_scalar(const EnvP& e, float x) {
     return 0.0f;
 }
 
-// 2^x.  The reference calls sleef pow (x16, process.rs:244) / libm powf (scalar, process.rs:227);
-// neither is reproducible bit-for-bit on a GPU.  Evaluating in binary64 and rounding once gives the
-// correctly rounded binary32 result in all but ~1e-8 of cases, which is what glibc returns too.
-__device__ __forceinline__ float pow2_ref(float x) { return (float)exp2((double)x); }
-__device__ __forceinline__ float exp_ref(float x) { return (float)exp((double)x); }
+// 2^x, e^x, sin/cos: s2_math.h (binary64 evaluation, one rounding).  The reference calls sleef pow
+// (x16, process.rs:244) / libm powf (scalar, process.rs:227) / expf / sinf / cosf, none reproducible
+// bit-for-bit on a GPU; their outputs only feed float results, compared with the north-star tolerance.
+__device__ __forceinline__ float pow2_ref(float x) { return s2_exp2f(x); }
+__device__ __forceinline__ float exp_ref(float x) { return s2_expf(x); }
 
 // process.rs:231-250.  amount == 0 -> pow(2, +-0) == 1 and 1 * f == f exactly: skip the call.
 __device__ __forceinline__ float modulate_freq(float f, float m, float amount) {
@@ -162,8 +163,8 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         float th = __fmul_rn(2.0f, pi);
         th = __fmul_rn(th, fl);
         th = __fdiv_rn(th, sr);
-        const float s = (float)sin((double)th);
-        const float co = (float)cos((double)th);
+        float s, co;
+        s2_sincosf(th, &s, &co);
         const float hd = __fdiv_rn(damp, 2.0f);
         const float num = __fsub_rn(1.0f, __fmul_rn(hd, s));
         const float den = __fadd_rn(1.0f, __fmul_rn(hd, s));
@@ -594,6 +595,45 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
 }
 
+// Modulated-cutoff chunk (one voice per lane): the period is constant but the mod envelope is moving,
+// so the cutoff — and with it the filter coefficients — changes every frame (process.rs:148-152,
+// 363-371; the first 200 ms of every note of the default patch, synth.rs:141-150).  Everything else
+// keeps its fast form; envelopes are evaluated per frame with their full stage chain.
+template <int FILTER, int KIND, int TRACE>
+__device__ __forceinline__ void chunk_modcut(FastV<1>& F, const EnvP* __restrict__ amp, const EnvP* __restrict__ mod,
+                                             float lpf, float amt_lpf, float damp, float sr, FiltC& fc, uint32_t kind,
+                                             uint32_t rot, uint32_t n0, float* __restrict__ row, const float* sintab) {
+    const EnvP A = *amp, M = *mod;
+    OscC o;
+    o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
+    FiltS fs = {F.x1, F.x2, F.y1, F.y2};
+    float ph = F.ph;
+    uint32_t n = n0;
+    float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
+#pragma unroll 1
+    for (int j = 0; j < kChunk / 4; j++) {
+        float o4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float g = env_x16(A, xf);
+            const float m = env_x16(M, xf);
+            const float fl = modulate_freq(lpf, m, amt_lpf);
+            if (__float_as_uint(fl) != fc.fl_bits) make_filt<FILTER>(fc, fl, damp, sr);
+            const float ph0 = ph;
+            const float osc = osc_step<KIND, false>(kind, o, ph, sintab);
+            const float nz = noise_fast(rot, n);
+            const float u = __fadd_rn(__fadd_rn(osc, F.gain), __fadd_rn(nz, F.namt));
+            const float y = filt_step<FILTER>(u, fc, fs);
+            o4[i] = TRACE == TRACE_PHASE ? ph0 : __fmul_rn(y, g);
+            n += 1u;
+            xf = __fadd_rn(xf, 1.0f);
+        }
+        *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+    F.ph = ph;
+    F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+}
+
 // General frame: the normative per-sample semantics, x16 or scalar-tail flavour.
 template <int FILTER, int TRACE>
 __device__ float general_frame(const Lane& L, float sr, uint32_t n, bool scalar_sem, OscC& o, FiltC& c,
@@ -804,12 +844,14 @@ render_kernel(const RenderArgs a) {
         const uint32_t cnt = min((uint32_t)kChunk, frames - t0);
         const bool full = cnt == kChunk && t0 + kChunk <= f16;
         bool warp_fast = full && fast_left >= (uint32_t)kChunk;
+        bool warp_semi = false;
         if (!warp_fast) {
-            bool lane_ok = true;
+            bool lane_ok = true, lane_semi_ok = true;
 #pragma unroll
             for (int e = 0; e < NV; e++) {
                 Cold& C = cold(e);
                 bool fast = active[e] && full;
+                bool semi = false;
                 if (fast && n[e] + kChunk > C.n_safe) {
                     // (Re)classify this voice: which envelope segments is frame n in, and until when.
                     fast = false;
@@ -822,6 +864,17 @@ render_kernel(const RenderArgs a) {
                     const int sm = env_stage(M, x0);
                     const bool mconst = !mm || sm == 2 || sm == 4;
                     uint32_t n_safe = 0u;
+                    if (NV == 1 && !mconst && C.L.amt_osc == 0.0f && ne + kChunk <= (1u << 24)) {
+                        // the mod envelope moves but only the cutoff follows it: the period is the
+                        // per-voice constant sr / pitch -> modulated-cutoff chunk
+                        OscC oc = C.oc;
+                        if (__float_as_uint(C.L.pitch) != oc.fo_bits) { make_osc(oc, C.L.pitch, sr); C.oc = oc; }
+                        if (oc.d < 1.0f && oc.P > 1.0f) {
+                            semi = true;
+                            vset(F.P, e, oc.P); vset(F.d, e, oc.d); vset(F.slope, e, oc.slope);
+                            vset(F.nhalf, e, -oc.half); vset(F.ts1, e, oc.ts1); vset(F.ts2, e, oc.ts2);
+                        }
+                    }
                     if (mconst && ne < (1u << 24)) {
                         const float ba = sa == 0 ? A.A : sa == 1 ? A.AD : sa == 2 ? A.Rs : sa == 3 ? A.E : 4.0e9f;
                         const float bm = !mm ? 4.0e9f : (sm == 2 ? M.Rs : 4.0e9f);
@@ -858,8 +911,10 @@ render_kernel(const RenderArgs a) {
                     C.n_safe = n_safe;
                 }
                 lane_ok &= fast || !active[e];
+                lane_semi_ok &= fast || semi || !active[e];
             }
             warp_fast = full && amask != 0u && __all_sync(0xffffffffu, lane_ok);
+            warp_semi = NV == 1 && !warp_fast && full && amask != 0u && __all_sync(0xffffffffu, lane_semi_ok);
             if (warp_fast) {
                 uint32_t lane_left = 0xffffffffu;
 #pragma unroll
@@ -909,6 +964,22 @@ render_kernel(const RenderArgs a) {
             }
 #pragma unroll
             for (int e = 0; e < NV; e++) n[e] += kChunk;
+        } else if (warp_semi) {
+            if constexpr (NV == 1) {
+                // voices that are fully constant run the same code: their cutoff simply does not move
+                Cold& C = cold(0);
+                FiltC fc = C.fc;
+                float* row = tile + lane * kTileStride;
+                const float lpf = C.L.lpf, amt = C.L.amt_lpf, damp = C.L.damp;
+                switch (wkind) {
+                case 0: chunk_modcut<FILTER, 0, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
+                case 1: chunk_modcut<FILTER, 1, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
+                case 2: chunk_modcut<FILTER, 2, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
+                default: chunk_modcut<FILTER, -1, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
+                }
+                if (active[0]) C.fc = fc;
+                n[0] += kChunk;
+            }
         } else {
 #pragma unroll
             for (int e = 0; e < NV; e++) {
@@ -973,11 +1044,27 @@ render_kernel(const RenderArgs a) {
             }
         }
         if (gbus) {
-            // synth.rs:176-202: voices are accumulated in slot order, starting from 0.0
             if ((uint32_t)lane < cnt) {
-                float acc = 0.0f;
+                float acc;
+                if (a.n_voices <= 32u) {
+                    // synth.rs:176-202: voices are accumulated in index order, starting from 0.0 — the
+                    // reference's exact summation order (a bank this narrow is one warp, identity slots)
+                    acc = 0.0f;
 #pragma unroll 8
-                for (int r = 0; r < kRows; r++) acc = __fadd_rn(acc, tile[r * kTileStride + lane]);
+                    for (int r = 0; r < kRows; r++) acc = __fadd_rn(acc, tile[r * kTileStride + lane]);
+                } else {
+                    // wide banks: fixed 4-way tree over the warp's rows (deterministic; four independent
+                    // chains instead of one 32-deep dependent chain)
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < kRows; r += 4) {
+                        a0 = __fadd_rn(a0, tile[(r + 0) * kTileStride + lane]);
+                        a1 = __fadd_rn(a1, tile[(r + 1) * kTileStride + lane]);
+                        a2 = __fadd_rn(a2, tile[(r + 2) * kTileStride + lane]);
+                        a3 = __fadd_rn(a3, tile[(r + 3) * kTileStride + lane]);
+                    }
+                    acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+                }
                 gbus[t0 + lane] = acc;
             }
         }
@@ -1010,13 +1097,46 @@ render_kernel(const RenderArgs a) {
     }
 }
 
-// bus[t] = ((0 + p_0[t]) + p_1[t]) + ... over warps in index order; coalesced over t.
-__global__ void bus_reduce_kernel(const float* __restrict__ partials, uint32_t n_warps, uint32_t frames,
+// Bus reduction, two stages, fixed summation tree (deterministic):
+//   stage 1  block (fx, sy) adds the 64 per-warp partial rows [64*sy, 64*sy + 64) for 32 frames: 8 threads
+//            per frame take 8 rows each (independent loads, index order), then the 8 sums are added in
+//            order -> seg[sy][t].  4,096 blocks at the bench shape: bandwidth-bound instead of the
+//            latency-bound single pass it replaces (51 us -> ~10 us for 32 MB of partials).
+//   stage 2  bus[t] = seg[0][t] + seg[1][t] + ... in order (n_seg <= a few dozen, L2-resident).
+// Reads are coalesced over t (128 bytes per row per warp).
+constexpr uint32_t kBusSegWarps = 64;
+
+__global__ void __launch_bounds__(256) bus_reduce_stage1(const float* __restrict__ partials, uint32_t n_warps,
+                                                         uint32_t frames, float* __restrict__ seg) {
+    __shared__ float sm[8][33];
+    const uint32_t tx = threadIdx.x & 31u, sub = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * 32u + tx;
+    const uint32_t w0 = blockIdx.y * kBusSegWarps + sub * 8u;
+    float acc = 0.0f;
+    if (t < frames) {
+        float v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; k++) v[k] = (w0 + k < n_warps) ? partials[(size_t)(w0 + k) * frames + t] : 0.0f;
+        acc = v[0];
+#pragma unroll
+        for (uint32_t k = 1; k < 8u; k++) acc = __fadd_rn(acc, v[k]);
+    }
+    sm[sub][tx] = acc;
+    __syncthreads();
+    if (sub == 0 && t < frames) {
+        float total = sm[0][tx];
+#pragma unroll
+        for (int k = 1; k < 8; k++) total = __fadd_rn(total, sm[k][tx]);
+        seg[(size_t)blockIdx.y * frames + t] = total;
+    }
+}
+
+__global__ void bus_reduce_stage2(const float* __restrict__ seg, uint32_t n_seg, uint32_t frames,
                                   float* __restrict__ bus) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= frames) return;
-    float acc = n_warps ? partials[t] : 0.0f;     // 0.0 + p_0 == p_0 (p_0 is never -0.0: it starts from +0.0)
-    for (uint32_t w = 1; w < n_warps; w++) acc = __fadd_rn(acc, partials[(size_t)w * frames + t]);
+    float acc = seg[t];
+    for (uint32_t k = 1; k < n_seg; k++) acc = __fadd_rn(acc, seg[(size_t)k * frames + t]);
     bus[t] = acc;
 }
 
@@ -1061,10 +1181,16 @@ cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, 
     return nv == 2 ? launch_nv<2>(a, filter_kind, trace, stream) : launch_nv<1>(a, filter_kind, trace, stream);
 }
 
-cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* bus,
-                              cudaStream_t stream) {
+uint32_t bus_segments(uint32_t n_warps) { return (n_warps + kBusSegWarps - 1) / kBusSegWarps; }
+
+cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
+                              float* bus, cudaStream_t stream) {
     if (frames == 0) return cudaSuccess;
-    bus_reduce_kernel<<<(frames + 255) / 256, 256, 0, stream>>>(partials, n_warps, frames, bus);
+    const uint32_t n_seg = bus_segments(n_warps);
+    bus_reduce_stage1<<<dim3((frames + 31) / 32, n_seg), 256, 0, stream>>>(partials, n_warps, frames, seg_scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    bus_reduce_stage2<<<(frames + 255) / 256, 256, 0, stream>>>(seg_scratch, n_seg, frames, bus);
     return cudaGetLastError();
 }
 
