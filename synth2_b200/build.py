@@ -12,8 +12,8 @@ import sys
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libs2cuda.so"
-SOURCES = [CSRC / "s2_kernels.cu", CSRC / "s2_capi.cu"]
-DEPS = SOURCES + [CSRC / "s2_internal.h", CSRC / "s2_math.h", CSRC / "sin_table_bits.inc",
+SOURCES = [CSRC / "s2_kernels.cu", CSRC / "s2_kernel_pc.cu", CSRC / "s2_capi.cu"]
+DEPS = SOURCES + [CSRC / "s2_internal.h", CSRC / "s2_device.cuh", CSRC / "s2_math.h", CSRC / "sin_table_bits.inc",
                   PKG.parent / "include" / "s2_cuda.h"]
 
 # -fmad=false / -prec-div / -prec-sqrt / -ftz=false: the render arithmetic is specified as
@@ -43,7 +43,8 @@ def stale():
 def build_lib(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    extra = os.environ.get("S2_NVCC_EXTRA", "").split()          # experiments, e.g. -DS2_TRIP=16
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

@@ -133,6 +133,7 @@ struct s2_bank {
     // the identity order, which also keeps the bus sum in the reference's voice order.
     std::vector<uint32_t> slot_of_voice, voice_of_slot;
     bool identity = true;
+    bool pc = false;              // producer/consumer warp pair per voice group (s2_kernel_pc.cu)
     int nv = 1;                   // voices per lane: 2 (packed f32x2 arithmetic) for banks wider than a warp
     uint32_t* d_stage = nullptr;  // staging for the bulk note-off table when slots are permuted
     uint64_t total_frames = 0;
@@ -191,7 +192,8 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     a.row_stride = row_stride;
     a.bus_partials = partials;
     a.has_sine = b->n_sine ? 1u : 0u;
-    CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
+    if (b->pc && trace == s2::TRACE_NONE) CUDA_TRY(s2::launch_render_pc(a, b->filter_kind, b->stream));
+    else CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
         CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, partials + (size_t)n_warps * frames,
@@ -277,9 +279,11 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->vpad = (n_voices + 63) & ~(size_t)63;
     b->book.resize(n_voices);
     b->nv = 1;   // 2 = two voices per lane with packed f32x2 math: fewer issue slots but half the warps; measured no faster
+    b->pc = false;   // measured slower than the one-warp kernel (profiles/r1_notes.md); S2_PC=1 selects it
+    if (const char* f = getenv("S2_PC")) b->pc = f[0] == '1';   // test hook
     if (const char* f = getenv("S2_FORCE_NV")) {          // test hook: exercise either lane width on any bank
         if (f[0] == '1') b->nv = 1;
-        if (f[0] == '2') b->nv = 2;
+        if (f[0] == '2') { b->nv = 2; b->pc = false; }
     }
 
     b->voice_of_slot.resize(n_voices);

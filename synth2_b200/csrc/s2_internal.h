@@ -55,6 +55,8 @@ constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, c
 // nv = voices per lane: 1 (scalar FP32) or 2 (packed f32x2); a warp renders 32*nv consecutive slots.
 cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, int nv, cudaStream_t stream);
 uint32_t render_warps(uint32_t n_voices, int nv);
+// producer/consumer warp pair per 32 voices (s2_kernel_pc.cu); same arguments, one voice per lane
+cudaError_t launch_render_pc(const RenderArgs& a, uint32_t filter_kind, cudaStream_t stream);
 // two kernels; seg_scratch holds bus_segments(n_warps) * frames floats
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
                               float* bus, cudaStream_t stream);
