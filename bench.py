@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--master-bus", action="store_true",
                     help="N>1: also mix every rank's voices and NCCL-reduce the whole-render bus to rank 0 "
                          "(BASELINE config 4), inside the timed region")
+    ap.add_argument("--pipeline", type=int, default=4,
+                    help="render each GPU's bank as this many voice ranges on internal streams (1 = single stream)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
@@ -227,6 +229,8 @@ def main():
     voices = bankgen.make_bank(V, RENDER_FRAMES, first_voice=rank * V, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     stream = torch.cuda.current_stream()
     bank = s2.VoiceBank(voices, SR, FILTER_BIQUAD, device=local, stream=stream)
+    if args.pipeline > 1:
+        bank.set_pipeline(args.pipeline)
     ring = [torch.empty((V, T), device=dev, dtype=torch.float32) for _ in range(2)]   # 2 x 1 GiB
     state0 = bank.get_state()
 
@@ -257,6 +261,7 @@ def main():
         for i, fr in enumerate(frames):
             bank.render(fr, ring[i & 1], T, master[pos:pos + fr] if want_master else None)
             pos += fr
+        bank.join(stream)            # pipelined banks: the timing stream waits for every voice range
         if want_master:
             dist.reduce(master, dst=0, op=dist.ReduceOp.SUM)
         ev1.record(stream)
@@ -297,6 +302,7 @@ def main():
         t0 = time.perf_counter()
         ev0.record(stream)
         e2e_pass(frames)
+        bank.join(stream)
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -342,7 +348,7 @@ def main():
                                    "60 s render in 4,096-frame blocks, state carried on device",
                        "voices_per_gpu": V, "block_frames": T, "render_frames": total_frames,
                        "l2_hygiene": "each step writes a fresh 1 GiB block (ring of 2) >> 126 MB L2; no input is re-read",
-                       "master_bus": bool(want_master)},
+                       "master_bus": bool(want_master), "pipeline_voice_ranges": int(args.pipeline)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }), flush=True)

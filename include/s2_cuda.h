@@ -134,6 +134,21 @@ int s2_bank_render_bus_host(s2_bank* bank, size_t frames, float* d_voice_out, si
 int s2_bank_render_bus_host_async(s2_bank* bank, size_t frames, float* d_voice_out, size_t row_stride,
                                   float* h_pinned_bus_out);
 
+/*
+ * Pipelined mode.  n_sub > 1 cuts the bank into n_sub contiguous voice ranges, each rendered on an
+ * internal stream, so consecutive s2_bank_render calls overlap across ranges instead of meeting at a
+ * device-wide barrier after every block (voices are independent: synth.rs:177-199).  Contract in this mode:
+ *   - render calls return at once and are ordered among themselves; their outputs are complete after
+ *     s2_bank_sync(), or, on a stream of the caller's, after s2_bank_join(bank, stream);
+ *   - the caller must not reuse an output buffer the bank may still be writing (join first);
+ *   - s2_bank_set_releases is pipelined too (each range applies the table before its next render);
+ *     every other entry (set_voice, release_voice, get/set_state, trace) drains the pipeline first;
+ *   - s2_bank_render_bus_host_async makes the bank's own stream (given at creation) wait for the copy.
+ * n_sub = 1 (default) keeps everything on the bank's stream.
+ */
+int s2_bank_set_pipeline(s2_bank* bank, int n_sub);
+int s2_bank_join(s2_bank* bank, void* stream);
+
 /* Checkpoint / restore / test hook.  Host arrays of n_voices entries; synchronises. */
 int s2_bank_get_state(s2_bank* bank, s2_voice_state* out);
 int s2_bank_set_state(s2_bank* bank, const s2_voice_state* in);

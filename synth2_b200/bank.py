@@ -100,6 +100,15 @@ class VoiceBank:
     def sync(self):
         check(lib().s2_bank_sync(self._h))
 
+    def set_pipeline(self, n_sub: int):
+        """n_sub > 1: render contiguous voice ranges on n_sub internal streams (see include/s2_cuda.h)."""
+        check(lib().s2_bank_set_pipeline(self._h, int(n_sub)))
+
+    def join(self, stream=None):
+        """Make `stream` (a torch stream, a raw cudaStream_t, or None = default) wait for the bank's work."""
+        sp = None if stream is None else C.c_void_p(getattr(stream, "cuda_stream", stream))
+        check(lib().s2_bank_join(self._h, sp))
+
     # -- carried state
     def get_state(self) -> np.ndarray:
         st = np.zeros(self.n_voices, dtype=VOICE_STATE)

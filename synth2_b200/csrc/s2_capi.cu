@@ -136,6 +136,24 @@ struct s2_bank {
     bool pc = false;              // producer/consumer warp pair per voice group (s2_kernel_pc.cu)
     int nv = 1;                   // voices per lane: 2 (packed f32x2 arithmetic) for banks wider than a warp
     uint32_t* d_stage = nullptr;  // staging for the bulk note-off table when slots are permuted
+    // Pipelined mode (s2_bank_set_pipeline): the bank is cut into n_sub contiguous slot ranges, each
+    // rendered on its own internal stream.  Consecutive render calls then overlap across sub-banks (no
+    // device-wide barrier between blocks), which keeps every SM sub-partition supplied with warps while
+    // the slower ones finish (profiles/r1_notes.md: +14 % at 65,536 voices).
+    int n_sub = 1;
+    cudaStream_t sub[8] = {};
+    cudaStream_t mix = nullptr;           // bus reduction and copies of the pipelined mode
+    cudaStream_t upload = nullptr;        // note-off table uploads (independent of the mix stream)
+    cudaEvent_t ev_gather[8][2] = {};     // sub-bank k has applied the table staged in buffer q
+    cudaEvent_t ev_sub[8] = {};           // last work issued on sub-stream k
+    cudaEvent_t ev_mix[2] = {};           // reduction of partial buffer p finished
+    cudaEvent_t ev_stage[2] = {};         // note-off table p has landed in its staging buffer
+    cudaEvent_t ev_tail = nullptr;        // last work issued on the mix stream
+    uint32_t* d_stage2[2] = {};
+    float* d_partials2[2] = {};
+    size_t partials2_cap = 0;
+    uint64_t step = 0, table_step = 0;
+    int table_pending = -1;               // staging buffer index holding a table not yet applied, or -1
     uint64_t total_frames = 0;
     uint64_t max_offset = 0;     // upper bound of any active voice's frame offset
     size_t n_sine = 0;
@@ -150,6 +168,91 @@ uint32_t current_offset(const s2_bank* b, size_t i) {
     return o > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)o;   // saturating_add, synth.rs:197
 }
 
+// Waits (on the host) for everything the bank has issued on its internal streams.
+int bank_drain(s2_bank* b) {
+    for (int k = 0; k < b->n_sub && b->n_sub > 1; k++) CUDA_TRY(cudaStreamSynchronize(b->sub[k]));
+    if (b->mix) CUDA_TRY(cudaStreamSynchronize(b->mix));
+    if (b->upload) CUDA_TRY(cudaStreamSynchronize(b->upload));
+    return S2_OK;
+}
+
+uint32_t sub_begin(const s2_bank* b, int k) {
+    // contiguous slot ranges, multiples of 64 slots so that warps (32 or 64 slots) never straddle two
+    const uint64_t groups = (b->n_voices + 63) / 64;
+    const uint64_t g = groups * (uint64_t)k / (uint64_t)b->n_sub;
+    const uint64_t s = g * 64;
+    return (uint32_t)(s < b->n_voices ? s : b->n_voices);
+}
+
+int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out) {
+    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
+    const int p = (int)(b->step & 1u);
+    float* partials = nullptr;
+    if (d_bus_out) {
+        const size_t need = ((size_t)n_warps + s2::bus_segments(n_warps)) * frames;
+        if (need > b->partials2_cap) {
+            int rc = bank_drain(b);
+            if (rc) return rc;
+            for (int i = 0; i < 2; i++) {
+                if (b->d_partials2[i]) CUDA_TRY(cudaFree(b->d_partials2[i]));
+                b->d_partials2[i] = nullptr;
+            }
+            b->partials2_cap = 0;
+            for (int i = 0; i < 2; i++) CUDA_TRY(cudaMalloc(&b->d_partials2[i], need * sizeof(float)));
+            b->partials2_cap = need;
+        }
+        partials = b->d_partials2[p];
+    }
+    s2::RenderArgs a;
+    a.params = b->d_params;
+    a.state = b->d_state;
+    a.n_voices = (uint32_t)b->n_voices;
+    a.vpad = (uint32_t)b->vpad;
+    a.sample_rate = (float)b->sample_rate;
+    a.frames = (uint32_t)frames;
+    a.voice_out = d_voice_out;
+    a.row_stride = row_stride;
+    a.bus_partials = partials;
+    a.has_sine = b->n_sine ? 1u : 0u;
+    uint32_t* release_row = reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad);
+    for (int k = 0; k < b->n_sub; k++) {
+        a.slot_begin = sub_begin(b, k);
+        a.slot_end = sub_begin(b, k + 1);
+        if (a.slot_begin >= a.slot_end) continue;
+        cudaStream_t sk = b->sub[k];
+        if (b->table_pending >= 0) {
+            // apply the staged note-off table to this sub-bank's slots, ordered between its own renders
+            CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_stage[b->table_pending], 0));
+            CUDA_TRY(s2::launch_gather_u32(b->d_stage2[b->table_pending],
+                                           b->d_params + (size_t)s2::P_ROW * b->vpad + a.slot_begin,
+                                           release_row + a.slot_begin, a.slot_end - a.slot_begin, sk));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaEventRecord(b->ev_gather[k][b->table_pending], sk));
+        }
+        if (d_bus_out && b->step >= 2) CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_mix[p], 0));   // partials[p] are free again
+        if (b->pc) CUDA_TRY(s2::launch_render_pc(a, b->filter_kind, sk));
+        else CUDA_TRY(s2::launch_render(a, b->filter_kind, s2::TRACE_NONE, b->nv, sk));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaEventRecord(b->ev_sub[k], sk));
+    }
+    b->table_pending = -1;
+    if (d_bus_out) {
+        for (int k = 0; k < b->n_sub; k++) CUDA_TRY(cudaStreamWaitEvent(b->mix, b->ev_sub[k], 0));
+        if (n_warps == 1) {
+            CUDA_TRY(cudaMemcpyAsync(d_bus_out, partials, frames * sizeof(float), cudaMemcpyDeviceToDevice, b->mix));
+        } else {
+            CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, partials + (size_t)n_warps * frames,
+                                           d_bus_out, b->mix));
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+        }
+        CUDA_TRY(cudaEventRecord(b->ev_mix[p], b->mix));
+    }
+    b->step++;
+    b->total_frames += frames;
+    b->max_offset += frames;
+    return S2_OK;
+}
+
 int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out,
                      int trace) {
     if (!b) return fail(S2_ERR_INVALID, "null bank");
@@ -162,6 +265,8 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     if (b->max_offset + frames > 0xFFFFFFFFull)
         return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
     CUDA_TRY(cudaSetDevice(b->device));
+    if (b->n_sub > 1 && trace == s2::TRACE_NONE) return bank_render_pipelined(b, frames, d_voice_out, row_stride, d_bus_out);
+    if (b->n_sub > 1) { int rc = bank_drain(b); if (rc) return rc; }
 
     const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
     float* partials = nullptr;
@@ -185,6 +290,8 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     a.params = b->d_params;
     a.state = b->d_state;
     a.n_voices = (uint32_t)b->n_voices;
+    a.slot_begin = 0;
+    a.slot_end = (uint32_t)b->n_voices;
     a.vpad = (uint32_t)b->vpad;
     a.sample_rate = (float)b->sample_rate;
     a.frames = (uint32_t)frames;
@@ -328,12 +435,27 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
 void s2_bank_destroy(s2_bank* b) {
     if (!b) return;
     cudaSetDevice(b->device);
+    bank_drain(b);
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_params);
     cudaFree(b->d_state);
     cudaFree(b->d_partials);
     cudaFree(b->d_bus);
     cudaFree(b->d_stage);
+    for (int k = 0; k < 8; k++) {
+        if (b->sub[k]) { cudaStreamSynchronize(b->sub[k]); cudaStreamDestroy(b->sub[k]); }
+        if (b->ev_sub[k]) cudaEventDestroy(b->ev_sub[k]);
+    }
+    if (b->mix) { cudaStreamSynchronize(b->mix); cudaStreamDestroy(b->mix); }
+    if (b->upload) { cudaStreamSynchronize(b->upload); cudaStreamDestroy(b->upload); }
+    for (int k = 0; k < 8; k++) for (int q = 0; q < 2; q++) if (b->ev_gather[k][q]) cudaEventDestroy(b->ev_gather[k][q]);
+    for (int i = 0; i < 2; i++) {
+        if (b->ev_mix[i]) cudaEventDestroy(b->ev_mix[i]);
+        if (b->ev_stage[i]) cudaEventDestroy(b->ev_stage[i]);
+        cudaFree(b->d_stage2[i]);
+        cudaFree(b->d_partials2[i]);
+    }
+    if (b->ev_tail) cudaEventDestroy(b->ev_tail);
     delete b;
 }
 
@@ -345,6 +467,7 @@ int s2_bank_set_voice(s2_bank* b, size_t index, const s2_voice_desc* voice) {
     int rc = validate_voice(*voice, index);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(b->device));
+    if ((rc = bank_drain(b)) != S2_OK) return rc;      // pipelined mode: per-voice edits are not pipelined
     float hp[s2::P_COUNT], hs[s2::S_COUNT];
     const size_t slot = b->slot_of_voice[index];   // the voice keeps its slot (a changed kind makes that warp mixed)
     pack_voice(*voice, (uint32_t)index, hp, 1);
@@ -369,6 +492,7 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
     if (!b) return fail(S2_ERR_INVALID, "null bank");
     if (index >= b->n_voices) return fail(S2_ERR_INVALID, "voice index %zu out of range", index);
     CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = bank_drain(b); if (rc) return rc; }
     const uint32_t rel = current_offset(b, index);   // release_frame_offset = current_frame_offset (synth.rs:75)
     CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad + b->slot_of_voice[index], &rel,
                              sizeof rel, cudaMemcpyHostToDevice, b->stream));
@@ -379,6 +503,24 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
 int s2_bank_set_releases(s2_bank* b, const uint32_t* h_release) {
     if (!b || !h_release) return fail(S2_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->device));
+    if (b->n_sub > 1) {
+        // stage the table on the mix stream; every sub-bank applies it to its own slots right before its
+        // next render (bank_render_pipelined), so no sub-bank waits for another
+        const int q = (int)(b->table_step & 1u);
+        if (b->table_pending >= 0) {
+            // two tables without a render in between: the older one is simply superseded
+            b->table_pending = -1;
+            b->table_step--;
+            return s2_bank_set_releases(b, h_release);
+        }
+        if (b->table_step >= 2)     // buffer q still feeds the gathers of the table staged two uploads ago
+            for (int k = 0; k < b->n_sub; k++) CUDA_TRY(cudaStreamWaitEvent(b->upload, b->ev_gather[k][q], 0));
+        CUDA_TRY(cudaMemcpyAsync(b->d_stage2[q], h_release, b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->upload));
+        CUDA_TRY(cudaEventRecord(b->ev_stage[q], b->upload));
+        b->table_pending = q;
+        b->table_step++;
+        return S2_OK;
+    }
     uint32_t* row = reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad);
     if (b->identity) {
         CUDA_TRY(cudaMemcpyAsync(row, h_release, b->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
@@ -421,6 +563,13 @@ int s2_bank_render_bus_host_async(s2_bank* b, size_t frames, float* d_voice_out,
     }
     int rc = bank_render_impl(b, frames, d_voice_out, row_stride, b->d_bus, s2::TRACE_NONE);
     if (rc) return rc;
+    if (b->n_sub > 1) {
+        // pipelined: the mix lives on the bank's mix stream; the caller's stream only waits for the copy
+        CUDA_TRY(cudaMemcpyAsync(h_bus_out, b->d_bus, frames * sizeof(float), cudaMemcpyDeviceToHost, b->mix));
+        CUDA_TRY(cudaEventRecord(b->ev_tail, b->mix));
+        CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_tail, 0));
+        return S2_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(h_bus_out, b->d_bus, frames * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     return S2_OK;
 }
@@ -428,6 +577,7 @@ int s2_bank_render_bus_host_async(s2_bank* b, size_t frames, float* d_voice_out,
 int s2_bank_get_state(s2_bank* b, s2_voice_state* out) {
     if (!b || !out) return fail(S2_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = bank_drain(b); if (rc) return rc; }
     std::vector<float> hs((size_t)s2::S_COUNT * b->vpad);
     CUDA_TRY(cudaMemcpyAsync(hs.data(), b->d_state, hs.size() * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -450,6 +600,7 @@ int s2_bank_get_state(s2_bank* b, s2_voice_state* out) {
 int s2_bank_set_state(s2_bank* b, const s2_voice_state* in) {
     if (!b || !in) return fail(S2_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = bank_drain(b); if (rc) return rc; }
     std::vector<float> hs((size_t)s2::S_COUNT * b->vpad, 0.0f);
     uint64_t mx = 0;
     for (size_t i = 0; i < b->n_voices; i++) {
@@ -467,7 +618,52 @@ int s2_bank_set_state(s2_bank* b, const s2_voice_state* in) {
 int s2_bank_sync(s2_bank* b) {
     if (!b) return fail(S2_ERR_INVALID, "null bank");
     CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = bank_drain(b); if (rc) return rc; }
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return S2_OK;
+}
+
+int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    if (n_sub < 1 || n_sub > 8) return fail(S2_ERR_INVALID, "n_sub must be in [1, 8]");
+    CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = s2_bank_sync(b); if (rc) return rc; }
+    if (n_sub > 1) {
+        for (int k = 0; k < n_sub; k++) {
+            if (!b->sub[k]) CUDA_TRY(cudaStreamCreateWithFlags(&b->sub[k], cudaStreamNonBlocking));
+            if (!b->ev_sub[k]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_sub[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(b->ev_sub[k], b->sub[k]));
+        }
+        if (!b->mix) CUDA_TRY(cudaStreamCreateWithFlags(&b->mix, cudaStreamNonBlocking));
+        if (!b->upload) CUDA_TRY(cudaStreamCreateWithFlags(&b->upload, cudaStreamNonBlocking));
+        for (int k = 0; k < n_sub; k++)
+            for (int q = 0; q < 2; q++)
+                if (!b->ev_gather[k][q]) {
+                    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_gather[k][q], cudaEventDisableTiming));
+                    CUDA_TRY(cudaEventRecord(b->ev_gather[k][q], b->sub[k]));
+                }
+        for (int i = 0; i < 2; i++) {
+            if (!b->ev_mix[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_mix[i], cudaEventDisableTiming));
+            if (!b->ev_stage[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_stage[i], cudaEventDisableTiming));
+            if (!b->d_stage2[i]) CUDA_TRY(cudaMalloc(&b->d_stage2[i], b->n_voices * sizeof(uint32_t)));
+        }
+        if (!b->ev_tail) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_tail, cudaEventDisableTiming));
+    }
+    b->n_sub = n_sub;
+    b->step = 0;
+    b->table_step = 0;
+    b->table_pending = -1;
+    return S2_OK;
+}
+
+int s2_bank_join(s2_bank* b, void* stream) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    if (b->n_sub <= 1) return S2_OK;       // everything already is on the bank's stream
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int k = 0; k < b->n_sub; k++) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_sub[k], 0));
+    CUDA_TRY(cudaEventRecord(b->ev_tail, b->mix));
+    CUDA_TRY(cudaStreamWaitEvent(st, b->ev_tail, 0));
     return S2_OK;
 }
 

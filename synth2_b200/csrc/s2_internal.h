@@ -37,7 +37,9 @@ enum TraceMode { TRACE_NONE = 0, TRACE_PHASE = 1 };
 struct RenderArgs {
     const float* params;   // [P_COUNT][vpad]
     float* state;          // [S_COUNT][vpad]
-    uint32_t n_voices;
+    uint32_t n_voices;     // voices in the whole bank
+    uint32_t slot_begin;   // this launch renders slots [slot_begin, slot_end): a sub-bank (multiple of 64) or the bank
+    uint32_t slot_end;
     uint32_t vpad;
     float sample_rate;     // `sample_rate.0 as f32` (filters.rs:17, units.rs:21)
     uint32_t frames;       // frames to render this launch

@@ -332,9 +332,9 @@ render_pc_kernel(const RenderArgs a) {
     __syncthreads();
     unsigned long long* bars = ctrl->bars;
 
-    const uint32_t gwarp = blockIdx.x;
-    const uint32_t vbase = gwarp * 32u;
-    if (vbase >= a.n_voices) return;
+    const uint32_t vbase = a.slot_begin + blockIdx.x * 32u;
+    if (vbase >= a.slot_end) return;
+    const uint32_t gwarp = vbase / 32u;
     ColdPc& C = *reinterpret_cast<ColdPc*>(cold_base + lane * kPcColdWords);
 
     // =============================================================== producer
@@ -368,7 +368,7 @@ render_pc_kernel(const RenderArgs a) {
     const uint32_t vp = a.vpad;
     const float sr = a.sample_rate;
     const uint32_t v = vbase + lane;
-    const bool exists = v < a.n_voices;
+    const bool exists = v < a.slot_end;
     const uint32_t vi = exists ? v : vbase;       // out-of-range lanes shadow slot vbase's loads, never store
     bool active;
     ConsState st;                                 // n, phase, filter state, current filter constants, gain level
@@ -576,7 +576,7 @@ render_pc_kernel(const RenderArgs a) {
 
 template <int FILTER>
 static cudaError_t launch_pc_t(const RenderArgs& a, cudaStream_t stream) {
-    const uint32_t blocks = (a.n_voices + 31u) / 32u;
+    const uint32_t blocks = (a.slot_end - a.slot_begin + 31u) / 32u;
     const size_t smem = kPcSmemFloats * sizeof(float) + (a.has_sine ? 4096 : 0);
     static bool attr_set = false;
     if (!attr_set) {

@@ -34,9 +34,9 @@ render_kernel(const RenderArgs a) {
         __syncthreads();
     }
 
-    const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
-    const uint32_t vbase = gwarp * kRows;
-    if (vbase >= a.n_voices) return;
+    const uint32_t vbase = a.slot_begin + (blockIdx.x * kWarpsPerBlock + warp) * kRows;
+    if (vbase >= a.slot_end) return;
+    const uint32_t gwarp = vbase / kRows;          // index of this voice group in the whole bank
     const uint32_t vp = a.vpad;
     const float sr = a.sample_rate;
     auto cold = [&](int e) -> Cold& { return *reinterpret_cast<Cold*>(cold_base + (e * 32 + lane) * kColdWords); };
@@ -48,7 +48,7 @@ render_kernel(const RenderArgs a) {
     for (int e = 0; e < NV; e++) {
         Cold& C = cold(e);
         const uint32_t v = vbase + e * 32 + lane;
-        const bool exists = v < a.n_voices;
+        const bool exists = v < a.slot_end;
         const uint32_t vi = exists ? v : vbase;    // out-of-range lanes shadow slot vbase's loads, never store
         const float* __restrict__ P = a.params + vi;
         active[e] = exists && __float_as_uint(P[P_ACTIVE * vp]) != 0u;
@@ -468,7 +468,7 @@ uint32_t render_warps(uint32_t n_voices, int nv) { return (n_voices + 32u * nv -
 
 template <int NV, int FILTER, int TRACE>
 static cudaError_t launch_t(const RenderArgs& a, cudaStream_t stream) {
-    const uint32_t n_warps = render_warps(a.n_voices, NV);
+    const uint32_t n_warps = render_warps(a.slot_end - a.slot_begin, NV);
     const uint32_t blocks = (n_warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const size_t smem = (size_t)kWarpsPerBlock * warp_smem_floats<NV>() * sizeof(float) + (a.has_sine ? 4096 : 0);
     static bool attr_set = false;
