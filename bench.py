@@ -140,7 +140,8 @@ def cpu_port_throughput(voices_desc, n_threads, frames, repeats=1):
     for _ in range(repeats):
         st = oracle.bank_init_states(voices_desc)
         t0 = time.perf_counter()
-        oracle.bank_render(voices_desc, st, SR, FILTER_BIQUAD, frames, want_voices=True, want_bus=False,
+        # per-thread scratch rows instead of a [V][frames] matrix: the sample can then be long enough
+        oracle.bank_render(voices_desc, st, SR, FILTER_BIQUAD, frames, want_voices=False, want_bus=False,
                            nthreads=n_threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
@@ -152,8 +153,8 @@ def cpu_baseline(args, bankgen):
     probe = bankgen.make_bank(max(cores * 4, 32), RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     rate, _ = cpu_port_throughput(probe, cores, 2048)
     want = max(rate * args.cpu_seconds, 1.0)
-    nv = max(cores * 32, 256)
-    frames = int(min(max(want / nv // BLOCK, 1), 64)) * BLOCK
+    nv = max(cores * 64, 1024)
+    frames = int(min(max(want / nv // BLOCK, 1), 720)) * BLOCK      # at most one 60 s render per voice
     sample = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     rate, dt = cpu_port_throughput(sample, cores, frames)
     return {"value": rate, "unit": "voice-samples/s", "cores": cores, "kind": "port",

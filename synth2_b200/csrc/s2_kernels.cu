@@ -12,13 +12,20 @@
 // Reference line numbers are relative to /root/reference/components/s2_lib/src/.
 #include "s2_device.cuh"
 
+// Register cap of the one-voice-per-lane kernel.  96 keeps the fast loops spill-free and lets 16+ one-warp
+// blocks share an SM, so blocks of overlapping launches (pipelined mode) find room: measured 1.079e12
+// voice-samples/s at 96 against 1.047e12 at 128 and 0.967e12 at 80 (spills).
+#ifndef S2_MAXREG
+#define S2_MAXREG 96
+#endif
+
 namespace s2 {
 
 // One warp renders 32*NV consecutive slots; lane l owns slots base + l (+ 32 for its second voice).
-// 65,536 voices = 13.8 one-warp blocks per SM: all of them must be resident at once (a second wave would
-// serialise), and at 144 registers only 13 fit (measured: +20 % time), so NV = 1 is held to 128.
+// 65,536 voices = 13.8 one-warp blocks per SM: without pipelining all of them must be resident at once (a
+// second wave would serialise: measured +20 % time at 144 registers, where only 13 fit).
 template <int NV, int FILTER, int TRACE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) __maxnreg__(NV == 1 ? 128 : 255)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) __maxnreg__(NV == 1 ? S2_MAXREG : 255)
 render_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5;
