@@ -56,7 +56,7 @@ def parse():
                     help="render each GPU's bank as this many voice ranges on internal streams (1 = single stream)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
 
 

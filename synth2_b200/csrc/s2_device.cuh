@@ -10,20 +10,15 @@
 #include "s2_internal.h"
 #include "s2_math.h"
 
-// 1: biquad products are fused into the running sum (FFMA); 0: every product and sum rounded
-// separately, as the source reads.  A resonant low-cutoff biquad in f32 direct form amplifies
-// per-frame rounding differences by ~1/(1-r) (~10^3 at 100 Hz, damping 0.2): the fused form drifted
-// 1.8e-4 from the oracle in tests, over the 1e-4 bar, so the unfused form is the default.
-#ifndef S2_FUSED_BIQUAD
-#define S2_FUSED_BIQUAD 0
-#endif
-// 1: the phase recurrence of a 32-frame chunk runs as its own pass ahead of everything else.
-// frames per straight-line trip of the time-packed loop (8, 16 or 32)
+// The biquad's products and sums are rounded separately, as the source reads (dsp_filters.rs:116-128).  A
+// fused (FFMA) form was tried and rejected: a resonant low-cutoff biquad in f32 direct form amplifies
+// per-frame rounding differences by ~1/(1-r) (~10^3 at 100 Hz, damping 0.2), enough to pass the 1e-4 bar.
+// (The fast phase step was also tried as a separate pass ahead of everything else: slower, row d of
+// profiles/r1_notes.md.)
+
+// Frames per straight-line trip of the time-packed loop; 16 and 32 measured no faster than 8.
 #ifndef S2_TRIP
 #define S2_TRIP 8
-#endif
-#ifndef S2_SPLIT_PHASE
-#define S2_SPLIT_PHASE 0
 #endif
 
 namespace s2 {
@@ -363,51 +358,14 @@ __device__ __forceinline__ void chunk_fast(FastV<NV>& F, const uint32_t (&kind)[
     vf<NV> xf;
 #pragma unroll
     for (int e = 0; e < NV; e++) { n[e] = n0[e]; vset(xf, e, __uint2float_rn(n0[e])); }   // exact: n0 + 32 <= 2^24
-#if S2_SPLIT_PHASE
-    // Pass A — the phase recurrence alone (try3/oscillators.rs:377-381): t = phase + 1/P; `% 1.0` is
-    // "subtract 1 when t >= 1" (t < 2, exact).  It is the only chain every other operation of a frame
-    // hangs from; running it first (32 frames, parked in the voice's own tile row) leaves pass B
-    // feed-forward except for the filter state, which the scheduler can software-pipeline.
-#pragma unroll 2
-    for (int j = 0; j < kChunk / 4; j++) {
-        float p4[NV][4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int e = 0; e < NV; e++) p4[e][i] = vget(F.ph, e);
-            const vf<NV> t = vadd(F.ph, F.d);
-            vf<NV> w;
-#pragma unroll
-            for (int e = 0; e < NV; e++) vset(w, e, vget(t, e) >= 1.0f ? 1.0f : 0.0f);
-            F.ph = vfma(w, none, t);                               // t - w, exact product
-        }
-#pragma unroll
-        for (int e = 0; e < NV; e++)
-            *reinterpret_cast<float4*>(tile + (e * 32 + lane) * kTileStride + 4 * j) =
-                make_float4(p4[e][0], p4[e][1], p4[e][2], p4[e][3]);
-    }
-#endif
     // 8 frames per trip: long enough for the scheduler to overlap neighbouring frames, short enough to
     // live in the instruction cache.
 #pragma unroll 2
     for (int j = 0; j < kChunk / 4; j++) {
         float o4[NV][4];
-#if S2_SPLIT_PHASE
-        float4 pin[NV];
-#pragma unroll
-        for (int e = 0; e < NV; e++)
-            pin[e] = *reinterpret_cast<const float4*>(tile + (e * 32 + lane) * kTileStride + 4 * j);
-#endif
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-#if S2_SPLIT_PHASE
-            vf<NV> ph0;
-#pragma unroll
-            for (int e = 0; e < NV; e++)
-                vset(ph0, e, i == 0 ? pin[e].x : i == 1 ? pin[e].y : i == 2 ? pin[e].z : pin[e].w);
-#else
             const vf<NV> ph0 = F.ph;
-#endif
             // ---- oscillator: x = period.mul_add(phase, 0); `% period` is a no-op (see osc_step)
             const vf<NV> x = vmul(F.P, ph0);
             vf<NV> osc;
@@ -448,14 +406,12 @@ __device__ __forceinline__ void chunk_fast(FastV<NV>& F, const uint32_t (&kind)[
                     vset(osc, e, y);
                 }
             }
-#if !S2_SPLIT_PHASE
             // ---- phase step: t = phase + 1/P; `% 1.0` == subtract 1 when t >= 1 (t < 2, exact)
             const vf<NV> t = vadd(ph0, F.d);
             vf<NV> w;
 #pragma unroll
             for (int e = 0; e < NV; e++) vset(w, e, vget(t, e) >= 1.0f ? 1.0f : 0.0f);
             F.ph = vfma(w, none, t);                               // t - w, exact product
-#endif
             // ---- noise (try3/hashnoise.rs:33-68): integer hash, then v/65535*2-1 (see noise_fast)
             vf<NV> v;
 #pragma unroll
@@ -479,16 +435,9 @@ __device__ __forceinline__ void chunk_fast(FastV<NV>& F, const uint32_t (&kind)[
                 // try3/dsp_filters.rs:116-128 (see filt_step): 2*(alpha*(x + 2*x1 + x2) + gamma*y1 - beta*y2)
                 vf<NV> sx = vfma(two, F.x1, u);
                 sx = vadd(sx, F.x2);
-#if S2_FUSED_BIQUAD
-                // products fused into the running sum (2 roundings fewer per frame, tolerance-level
-                // difference from the unfused source; only y1 sits on the frame-to-frame critical path)
-                const vf<NV> r = vfma(F.c1, F.y2, vmul(F.c0, sx));          // c1 holds -2*beta
-                y = vfma(F.c2, F.y1, r);
-#else
                 vf<NV> tt = vmul(F.c0, sx);
                 tt = vadd(tt, vmul(F.c2, F.y1));
                 y = vadd(tt, vmul(F.c1, F.y2));                             // c1 holds -2*beta: exact negation
-#endif
                 F.x2 = F.x1; F.x1 = u; F.y2 = F.y1; F.y1 = y;
             }
             // ---- amp envelope (old/simdtest.rs:270-330 on one segment) and gain (process.rs:373-378)

@@ -379,8 +379,9 @@ def test_split_invariance_bitwise():
 
 @pytest.mark.parametrize("filter_kind", [0, 1])
 def test_lane_widths_agree_bitwise(filter_kind, monkeypatch):
-    """NV = 1 (time-packed) and NV = 2 (voice-packed) kernels perform the same IEEE operations per voice:
-    identical bits, including through envelope ramps, modulated segments and the scalar tail."""
+    """The three kernel layouts — NV = 1 (time-packed, default), NV = 2 (voice-packed), producer/consumer
+    warp pair — perform the same IEEE operations per voice: identical bits, including through envelope
+    ramps, modulated segments and the scalar tail."""
     frames = [4096, 4096, 2048, 1000]
     v = bank_for(filter_kind, 160, sum(frames), kinds=(0, 1, 2, 3))
     v["noise_amt"] = (np.arange(160) % 2) * 0.5
@@ -391,12 +392,17 @@ def test_lane_widths_agree_bitwise(filter_kind, monkeypatch):
         monkeypatch.setenv("S2_FORCE_NV", nv)
         outs[nv] = gpu_bank_render(v, filter_kind, frames)
     monkeypatch.delenv("S2_FORCE_NV")
-    a, b = outs["1"], outs["2"]
-    bad = np.argwhere(a[0] != b[0])
-    assert bad.size == 0, f"first differing (voice, frame): {bad[:5].tolist()}"
-    assert a[2].tobytes() == b[2].tobytes()
-    scale = max(1.0, float(np.max(np.abs(a[1]))))
-    assert float(np.max(np.abs(a[1] - b[1]))) <= 1e-5 * scale     # bus: different slot grouping, same voices
+    monkeypatch.setenv("S2_PC", "1")           # producer/consumer warp pair per voice group (s2_kernel_pc.cu)
+    outs["pc"] = gpu_bank_render(v, filter_kind, frames)
+    monkeypatch.delenv("S2_PC")
+    a = outs["1"]
+    for name in ("2", "pc"):
+        b = outs[name]
+        bad = np.argwhere(a[0] != b[0])
+        assert bad.size == 0, f"{name}: first differing (voice, frame): {bad[:5].tolist()}"
+        assert a[2].tobytes() == b[2].tobytes()
+        scale = max(1.0, float(np.max(np.abs(a[1]))))
+        assert float(np.max(np.abs(a[1] - b[1]))) <= 1e-5 * scale     # bus: different row grouping, same voices
 
 
 @pytest.mark.parametrize("n_sub", [2, 4, 8])
@@ -464,6 +470,62 @@ def test_pipelined_back_to_back_without_sync():
         rowsum = ring[i].double().sum(dim=0).cpu().numpy()
         scale = max(1.0, float(np.max(np.abs(rowsum))))
         assert float(np.max(np.abs(host_bus[i].numpy() - rowsum))) <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_banks_against_oracle(seed):
+    """Seeded random patches, offsets, release points, block splits, lane layouts and pipelining."""
+    rng = np.random.default_rng(1000 + seed)
+    fk = int(rng.integers(0, 2))
+    V = int(rng.choice([1, 7, 32, 33, 96, 130, 257]))
+    frames = [int(x) for x in rng.choice([16, 48, 250, 512, 1000, 2048, 3001], size=int(rng.integers(1, 4)))]
+    v = s2.default_voice(V)
+    v["active"] = (rng.random(V) > 0.1).astype(np.uint32)
+    v["osc_kind"] = rng.integers(0, 4, V)
+    v["noise_seed"] = rng.integers(0, 2 ** 32, V, dtype=np.uint64).astype(np.uint32)
+    v["pitch_hz"] = [s2.note_to_pitch(int(n)) for n in rng.integers(12, 120, V)]
+    v["osc_gain"] = rng.choice([0.0, 0.5, 1.0], V).astype(np.float32)
+    v["noise_amt"] = rng.choice([0.0, 0.0, 0.3, 1.0], V).astype(np.float32)
+    v["lpf_freq_hz"] = np.exp(rng.uniform(np.log(150.0), np.log(6000.0), V)).astype(np.float32)
+    v["damping"] = rng.uniform(0.3, 1.414, V).astype(np.float32)
+    for env, lo in (("amp", 0.0), ("mod", 0.0)):
+        v[f"{env}_attack_ms"] = rng.choice([0.0, 1.0, 7.3, 40.0], V).astype(np.float32)
+        v[f"{env}_decay_ms"] = rng.choice([0.0, 3.0, 25.0, 90.0], V).astype(np.float32)
+        v[f"{env}_sustain"] = rng.uniform(lo, 1.0, V).astype(np.float32)
+        v[f"{env}_release_ms"] = rng.choice([0.0, 2.0, 30.0], V).astype(np.float32)
+    v["mod_env_to_lpf_freq"] = rng.choice([0.0, 0.0, 1.0, -1.5], V).astype(np.float32) if fk else \
+        rng.choice([0.0, 10.0, -3.0, 4.5], V).astype(np.float32)
+    v["mod_env_to_osc_freq"] = 0.0
+    start = int(rng.choice([0, 0, 16, 4800, (1 << 24) - 700]))
+    v["frame_offset"] = start + 16 * rng.integers(0, 4, V)
+    rel = v["frame_offset"] + rng.integers(0, sum(frames) + 200, V)
+    v["release_offset"] = np.where(rng.random(V) < 0.3, s2.NO_RELEASE, rel).astype(np.uint32)
+    ref, rbus, rst = oracle_bank_render(v, fk, frames)
+    mode = seed % 4
+    env = {1: ("S2_FORCE_NV", "2"), 2: ("S2_PC", "1")}.get(mode)
+    import os
+    if env:
+        os.environ[env[0]] = env[1]
+    try:
+        if mode == 3:
+            outs = []
+            with s2.VoiceBank(v, SR, fk) as bank:
+                bank.set_pipeline(3)
+                for fr in frames:
+                    stride = (fr + 3) & ~3
+                    vo = torch.full((V, stride), float("nan"), device="cuda")
+                    bank.render(fr, vo, stride, None)
+                    bank.sync()
+                    outs.append(vo[:, :fr].cpu().numpy())
+                gst = bank.get_state()
+            got = np.concatenate(outs, axis=1)
+        else:
+            got, gbus, gst = gpu_bank_render(v, fk, frames)
+    finally:
+        if env:
+            del os.environ[env[0]]
+    assert_parity(ref, got, f"fuzz seed {seed} fk {fk} V {V} frames {frames} mode {mode}")
+    assert_state_parity(gst, rst, fk)
 
 
 def test_errors_are_reported_not_crashes():

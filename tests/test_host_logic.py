@@ -221,3 +221,18 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_math_kernels_round_once_on_cpu(tmp_path):
+    """synth2_b200/csrc/s2_math.h (2^x, e^x, sin/cos used for filter coefficients) is host-and-device code:
+    compiled for the CPU it must return the once-rounded binary64 result on dense sweeps (tools/check_math.cpp)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "check_math"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-march=x86-64-v3", "-o", str(exe),
+                    str(ROOT / "tools" / "check_math.cpp")], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout
+    assert "special values ok" in out.stdout
