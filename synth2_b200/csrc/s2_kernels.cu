@@ -331,37 +331,66 @@ render_kernel(const RenderArgs a) {
             }
         }
         __syncwarp();
-        if (gout) {
+        // (16-byte stores into this warp's partial row: needs frames % 4 == 0 and an aligned base)
+        const bool wide_bus = gbus != nullptr && a.n_voices > 32u && cnt == kChunk && (frames & 3u) == 0u &&
+                              (reinterpret_cast<uintptr_t>(gbus) & 15u) == 0u;
+        float4 bsum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (cnt == kChunk && (gout || wide_bus)) {
+            // One pass over the tile, transposed: lane (q, c4) reads 16 bytes of rows 4*i + q.  For banks
+            // wider than a warp the same registers also feed the bus: each lane adds its 8*NV rows, then the
+            // four q-groups are added by two butterfly shuffles (a fixed tree: deterministic; banks of <= 32
+            // voices use the reference's sequential order below).  Three straight-line variants so that the
+            // common one carries no predicates.
             const size_t tb = (size_t)t0 * sizeof(float);
             const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(cold_base + kRows * kColdWords);
-            if (cnt == kChunk && all_rows) {
+            if (all_rows && !wide_bus) {
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
                     char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
                     const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
                     __stcs(reinterpret_cast<float4*>(dst + tb), val);
                 }
-            } else if (cnt == kChunk) {
+            } else if (all_rows) {
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
                     char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
-                    if (dst) {
-                        const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
-                        __stcs(reinterpret_cast<float4*>(dst + tb), val);
-                    }
+                    const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                    __stcs(reinterpret_cast<float4*>(dst + tb), val);
+                    bsum.x = __fadd_rn(bsum.x, val.x); bsum.y = __fadd_rn(bsum.y, val.y);
+                    bsum.z = __fadd_rn(bsum.z, val.z); bsum.w = __fadd_rn(bsum.w, val.w);
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < NV; e++) {
-                    for (uint32_t r = 0; r < 32u; r++) {
-                        const uint32_t orow = __shfl_sync(0xffffffffu, cold(e).out_row, r);
-                        if (orow != 0xffffffffu && (uint32_t)lane < cnt)
-                            gout[(size_t)orow * stride + t0 + lane] = tile[(e * 32 + r) * kTileStride + lane];
+                for (int i = 0; i < 8 * NV; i++) {
+                    const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                    if (gout) {
+                        char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
+                        if (dst) __stcs(reinterpret_cast<float4*>(dst + tb), val);
                     }
+                    bsum.x = __fadd_rn(bsum.x, val.x); bsum.y = __fadd_rn(bsum.y, val.y);
+                    bsum.z = __fadd_rn(bsum.z, val.z); bsum.w = __fadd_rn(bsum.w, val.w);
+                }
+            }
+        } else if (gout) {
+#pragma unroll
+            for (int e = 0; e < NV; e++) {
+                for (uint32_t r = 0; r < 32u; r++) {
+                    const uint32_t orow = __shfl_sync(0xffffffffu, cold(e).out_row, r);
+                    if (orow != 0xffffffffu && (uint32_t)lane < cnt)
+                        gout[(size_t)orow * stride + t0 + lane] = tile[(e * 32 + r) * kTileStride + lane];
                 }
             }
         }
-        if (gbus) {
+        if (wide_bus) {
+#pragma unroll
+            for (int sh = 8; sh <= 16; sh <<= 1) {
+                bsum.x = __fadd_rn(bsum.x, __shfl_xor_sync(0xffffffffu, bsum.x, sh));
+                bsum.y = __fadd_rn(bsum.y, __shfl_xor_sync(0xffffffffu, bsum.y, sh));
+                bsum.z = __fadd_rn(bsum.z, __shfl_xor_sync(0xffffffffu, bsum.z, sh));
+                bsum.w = __fadd_rn(bsum.w, __shfl_xor_sync(0xffffffffu, bsum.w, sh));
+            }
+            if (lane < 8) *reinterpret_cast<float4*>(gbus + t0 + c4) = bsum;
+        } else if (gbus) {
             if ((uint32_t)lane < cnt) {
                 float acc;
                 if (a.n_voices <= 32u) {
@@ -371,8 +400,7 @@ render_kernel(const RenderArgs a) {
 #pragma unroll 8
                     for (int r = 0; r < kRows; r++) acc = __fadd_rn(acc, tile[r * kTileStride + lane]);
                 } else {
-                    // wide banks: fixed 4-way tree over the warp's rows (deterministic; four independent
-                    // chains instead of one 32-deep dependent chain)
+                    // ragged last chunk of a wide bank: fixed 4-way tree over the warp's rows
                     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
                     for (int r = 0; r < kRows; r += 4) {
