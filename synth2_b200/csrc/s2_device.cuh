@@ -97,6 +97,28 @@ __device__ __forceinline__ float env_x16(const E& e, float x) {
     }
 }
 
+// The envelope segment a frame offset lies in, as the line g = es * (x - ex0) + ey0 that reproduces that
+// stage's formula bit-for-bit (attack: (1/A)*x + 0; decay: ((S-1)/D)*(x-A) + 1; sustain: 0*x + S; release:
+// ((-S)/R)*(x-Rs) + S; end: 0*x + 0), valid for frame offsets [.., nend).  Offsets below 2^24 only
+// (x = (f32)n exact; nend = first integer whose f32 image reaches the stage boundary).
+struct SegEnv { float es, nex0, ey0; uint32_t nend; };
+
+template <class E>
+__device__ __forceinline__ SegEnv seg_env(const E& e, uint32_t n) {
+    const float x = __uint2float_rn(n);
+    const int st = env_stage(e, x);
+    SegEnv s;
+    s.es = st == 0 ? e.sA : st == 1 ? e.sD : st == 3 ? e.sR : 0.0f;
+    s.nex0 = st == 1 ? -e.A : st == 3 ? -e.Rs : -0.0f;             // x + (-0.0) == x
+    s.ey0 = st == 1 ? 1.0f : (st == 2 || st == 3) ? e.S : 0.0f;
+    const float b = st == 0 ? e.A : st == 1 ? e.AD : st == 2 ? e.Rs : st == 3 ? e.E : 4.0e9f;
+    s.nend = min(__float2uint_ru(b), 1u << 24);
+    return s;
+}
+__device__ __forceinline__ float seg_eval(const SegEnv& s, float x) {
+    return __fadd_rn(__fmul_rn(s.es, __fadd_rn(x, s.nex0)), s.ey0);
+}
+
 // math.rs:11-19 with feature "fma"
 __device__ __forceinline__ float line_fma(float rise, float run, float x, float y0) {
     return __fmaf_rn(__fdiv_rn(rise, run), x, y0);
@@ -478,7 +500,9 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
     uint32_t n = n0;
     float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
     EnvP A;
-    if (!GCONST) A = *amp;
+    SegEnv sg = {0.0f, 0.0f, 0.0f, 0u};
+    uint32_t ne = n0;                                             // frame offset of the next envelope pair
+    if (!GCONST) { A = *amp; sg = seg_env(A, n0); }
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
     fc.c0 = F.c0; fc.c1 = FILTER == 0 ? F.c1 : -F.c1; fc.c2 = F.c2; fc.fl_bits = 0;   // F.c1 holds -2*beta for the biquad
@@ -556,8 +580,18 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             float2 g2;
             if (GCONST) g2 = ey0_2;
             else {
-                g2.x = env_x16(A, xf);
-                g2.y = env_x16(A, __fadd_rn(xf, 1.0f));
+                const float xb = __fadd_rn(xf, 1.0f);
+                if (ne + 2u <= sg.nend) {
+                    // both frames inside the current segment: its line, bit-exact (see SegEnv)
+                    g2.x = seg_eval(sg, xf);
+                    g2.y = seg_eval(sg, xb);
+                } else {
+                    // a stage boundary: the full stage chain for these two frames, then the next segment
+                    g2.x = env_x16(A, xf);
+                    g2.y = env_x16(A, xb);
+                    sg = seg_env(A, ne + 2u);
+                }
+                ne += 2u;
                 xf = __fadd_rn(xf, 2.0f);
             }
             const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(make_float2(ya, yb), g2);
@@ -581,6 +615,7 @@ __device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict_
                                              float lpf, float amt_lpf, float damp, float sr, FiltC& fc, uint32_t kind,
                                              uint32_t rot, uint32_t n0, float* __restrict__ row, const float* sintab) {
     const ENV A = *amp, M = *mod;
+    SegEnv sa = seg_env(A, n0), sm = seg_env(M, n0);
     OscC o;
     o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
@@ -592,10 +627,14 @@ __device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict_
         float o4[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const float g = env_x16(A, xf);
-            const float m = env_x16(M, xf);
-            const float fl = modulate_freq(lpf, m, amt_lpf);
-            if (__float_as_uint(fl) != fc.fl_bits) make_filt<FILTER>(fc, fl, damp, sr);
+            float g, m;
+            if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(A, xf); sa = seg_env(A, n + 1u); }
+            if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
+            // branch-free on purpose: 2^(m * 0) * f == f exactly, and re-deriving unchanged coefficients
+            // gives the same bits, so voices whose cutoff does not move lose nothing and the warp does not
+            // diverge around the binary64 code
+            const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
+            make_filt<FILTER>(fc, fl, damp, sr);
             const float ph0 = ph;
             const float osc = osc_step<KIND, false>(kind, o, ph, sintab);
             const float nz = noise_fast(rot, n);
