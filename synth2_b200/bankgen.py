@@ -80,3 +80,62 @@ def make_bank(n_voices: int, render_frames: int, first_voice: int = 0, kinds=(OS
     b["release_offset"] = rel if rel > 0 else NO_RELEASE
     b["active"] = 1
     return b
+
+
+# ---- BASELINE config 5: patch-variant sweep -----------------------------------
+
+SWEEP_AXIS = 32                      # 32 cutoffs x 32 dampings x 32 detunes = 32,768 variants per GPU
+SWEEP_VARIANTS = SWEEP_AXIS ** 3
+
+
+def sweep_axes(sample_rate: int = 48000):
+    """The three grid axes, as the f32 values both sides use: cutoff log-spaced 100 Hz..12.8 kHz (7 octaves),
+    damping linear 0.2..1.414 (dsp_filters.rs:95: 0.2 is the minimum, sqrt(2) neutral), detune linear
+    -50..+50 cents."""
+    i = np.arange(SWEEP_AXIS, dtype=np.float64) / (SWEEP_AXIS - 1)
+    cutoff = (100.0 * np.exp2(7.0 * i)).astype(np.float32)
+    damping = (0.2 + (1.414 - 0.2) * i).astype(np.float32)
+    cents = -50.0 + 100.0 * i
+    return cutoff, damping, cents
+
+
+def make_sweep_bank(gpu_index: int, render_frames: int, first_variant: int = 0, n_variants: int = None,
+                    sample_rate: int = 48000, kind=OSC_SAW) -> np.ndarray:
+    """Variants [first_variant, first_variant + n_variants) of GPU `gpu_index`'s share of the sweep.
+
+    Variant id = (cutoff_index * 32 + damping_index) * 32 + detune_index.  Every variant is the default patch
+    (synth.rs:125-152: amp ADSR 100/100/0.5/100 ms, mod ADSR 0/200/0/0 ms, gain 1, noise 0, seed 0) played at
+    MIDI note 48 + 4 * gpu_index, detuned: pitch = f32(note_to_pitch(note) * 2^(cents/1200)).  The mod envelope
+    opens the cutoff by up to 1.5 octaves but never beyond 0.45 * sample_rate (the 2nd-order low-pass is
+    unstable above Nyquist): amount = clamp(log2(0.45 * sr / cutoff), 0, 1.5).  Note-on at frame 0, release
+    at 75 % of the render rounded down to a multiple of 16.
+    """
+    if n_variants is None:
+        n_variants = SWEEP_VARIANTS - first_variant
+    if not (0 <= first_variant and first_variant + n_variants <= SWEEP_VARIANTS):
+        raise ValueError("variant range outside the 32 x 32 x 32 grid")
+    cutoff, damping, cents = sweep_axes(sample_rate)
+    vid = np.arange(first_variant, first_variant + n_variants, dtype=np.int64)
+    ci, di, ti = vid // (SWEEP_AXIS * SWEEP_AXIS), (vid // SWEEP_AXIS) % SWEEP_AXIS, vid % SWEEP_AXIS
+    note = 48 + 4 * int(gpu_index)
+    if not 0 <= note < 128:
+        raise ValueError("gpu_index out of range for a MIDI note")
+    base = float(np.float32(note_to_pitch(note)))
+    b = default_bank(n_variants)
+    b["osc_kind"] = kind
+    b["pitch_hz"] = (base * np.exp2(cents[ti] / 1200.0)).astype(np.float32)
+    b["lpf_freq_hz"] = cutoff[ci]
+    b["damping"] = damping[di]
+    room = np.log2(0.45 * float(sample_rate) / cutoff[ci].astype(np.float64))
+    b["mod_env_to_lpf_freq"] = np.clip(room, 0.0, 1.5).astype(np.float32)
+    rel = (int(render_frames) * 3 // 4) & ~15
+    b["release_offset"] = rel if rel > 0 else NO_RELEASE
+    b["frame_offset"] = 0
+    b["active"] = 1
+    return b
+
+
+def default_bank(n: int) -> np.ndarray:
+    """n copies of `Synth::default_config()` (synth.rs:125-152), inactive, as written by the library."""
+    from .bank import default_voice
+    return default_voice(n)

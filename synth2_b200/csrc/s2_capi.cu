@@ -112,6 +112,11 @@ struct VoiceBook {           // host mirror of what the device will hold, O(1) p
 
 }  // namespace
 
+// Partial-sum buffers of the pipelined mix.  The reduction of step i runs on the (high-priority) mix stream
+// while the sub-banks already render step i+1; with only two buffers step i+2 would have to wait for it,
+// and a reduction that is slow to get SM slots next to the render blocks then stalls the whole pipeline.
+constexpr int kMixBufs = 4;
+
 struct s2_bank {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -146,11 +151,11 @@ struct s2_bank {
     cudaStream_t upload = nullptr;        // note-off table uploads (independent of the mix stream)
     cudaEvent_t ev_gather[8][2] = {};     // sub-bank k has applied the table staged in buffer q
     cudaEvent_t ev_sub[8] = {};           // last work issued on sub-stream k
-    cudaEvent_t ev_mix[2] = {};           // reduction of partial buffer p finished
+    cudaEvent_t ev_mix[kMixBufs] = {};    // reduction of partial buffer p finished
     cudaEvent_t ev_stage[2] = {};         // note-off table p has landed in its staging buffer
     cudaEvent_t ev_tail = nullptr;        // last work issued on the mix stream
     uint32_t* d_stage2[2] = {};
-    float* d_partials2[2] = {};
+    float* d_partials2[kMixBufs] = {};
     size_t partials2_cap = 0;
     uint64_t step = 0, table_step = 0;
     int table_pending = -1;               // staging buffer index holding a table not yet applied, or -1
@@ -186,19 +191,19 @@ uint32_t sub_begin(const s2_bank* b, int k) {
 
 int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out) {
     const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
-    const int p = (int)(b->step & 1u);
+    const int p = (int)(b->step % (uint64_t)kMixBufs);
     float* partials = nullptr;
     if (d_bus_out) {
         const size_t need = ((size_t)n_warps + s2::bus_segments(n_warps)) * frames;
         if (need > b->partials2_cap) {
             int rc = bank_drain(b);
             if (rc) return rc;
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < kMixBufs; i++) {
                 if (b->d_partials2[i]) CUDA_TRY(cudaFree(b->d_partials2[i]));
                 b->d_partials2[i] = nullptr;
             }
             b->partials2_cap = 0;
-            for (int i = 0; i < 2; i++) CUDA_TRY(cudaMalloc(&b->d_partials2[i], need * sizeof(float)));
+            for (int i = 0; i < kMixBufs; i++) CUDA_TRY(cudaMalloc(&b->d_partials2[i], need * sizeof(float)));
             b->partials2_cap = need;
         }
         partials = b->d_partials2[p];
@@ -229,7 +234,7 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
             g_launches.fetch_add(1, std::memory_order_relaxed);
             CUDA_TRY(cudaEventRecord(b->ev_gather[k][b->table_pending], sk));
         }
-        if (d_bus_out && b->step >= 2) CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_mix[p], 0));   // partials[p] are free again
+        if (d_bus_out && b->step >= (uint64_t)kMixBufs) CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_mix[p], 0));   // partials[p] are free again
         if (b->pc) CUDA_TRY(s2::launch_render_pc(a, b->filter_kind, sk));
         else CUDA_TRY(s2::launch_render(a, b->filter_kind, s2::TRACE_NONE, b->nv, sk));
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -450,9 +455,11 @@ void s2_bank_destroy(s2_bank* b) {
     if (b->upload) { cudaStreamSynchronize(b->upload); cudaStreamDestroy(b->upload); }
     for (int k = 0; k < 8; k++) for (int q = 0; q < 2; q++) if (b->ev_gather[k][q]) cudaEventDestroy(b->ev_gather[k][q]);
     for (int i = 0; i < 2; i++) {
-        if (b->ev_mix[i]) cudaEventDestroy(b->ev_mix[i]);
         if (b->ev_stage[i]) cudaEventDestroy(b->ev_stage[i]);
         cudaFree(b->d_stage2[i]);
+    }
+    for (int i = 0; i < kMixBufs; i++) {
+        if (b->ev_mix[i]) cudaEventDestroy(b->ev_mix[i]);
         cudaFree(b->d_partials2[i]);
     }
     if (b->ev_tail) cudaEventDestroy(b->ev_tail);
@@ -634,7 +641,11 @@ int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
             if (!b->ev_sub[k]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_sub[k], cudaEventDisableTiming));
             CUDA_TRY(cudaEventRecord(b->ev_sub[k], b->sub[k]));
         }
-        if (!b->mix) CUDA_TRY(cudaStreamCreateWithFlags(&b->mix, cudaStreamNonBlocking));
+        if (!b->mix) {
+            int prio_lo = 0, prio_hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&b->mix, cudaStreamNonBlocking, prio_hi));
+        }
         if (!b->upload) CUDA_TRY(cudaStreamCreateWithFlags(&b->upload, cudaStreamNonBlocking));
         for (int k = 0; k < n_sub; k++)
             for (int q = 0; q < 2; q++)
@@ -642,8 +653,9 @@ int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
                     CUDA_TRY(cudaEventCreateWithFlags(&b->ev_gather[k][q], cudaEventDisableTiming));
                     CUDA_TRY(cudaEventRecord(b->ev_gather[k][q], b->sub[k]));
                 }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kMixBufs; i++)
             if (!b->ev_mix[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_mix[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
             if (!b->ev_stage[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_stage[i], cudaEventDisableTiming));
             if (!b->d_stage2[i]) CUDA_TRY(cudaMalloc(&b->d_stage2[i], b->n_voices * sizeof(uint32_t)));
         }

@@ -24,6 +24,23 @@ namespace s2 {
 // One warp renders 32*NV consecutive slots; lane l owns slots base + l (+ 32 for its second voice).
 // 65,536 voices = 13.8 one-warp blocks per SM: without pipelining all of them must be resident at once (a
 // second wave would serialise: measured +20 % time at 144 registers, where only 13 fit).
+// Sum of a lane's N float4 tile reads as a pairwise tree of packed adds (depth log2 N instead of a chain of
+// N: the adds sit at the end of a chunk where the warp has nothing else to issue).  Fixed order: deterministic.
+template <int N>
+__device__ __forceinline__ void tree_sum_rows(float4 (&val)[N], float2& b01, float2& b23) {
+#pragma unroll
+    for (int w = 1; w < N; w <<= 1) {
+#pragma unroll
+        for (int i = 0; i + w < N; i += 2 * w) {
+            const float2 lo = padd2(make_float2(val[i].x, val[i].y), make_float2(val[i + w].x, val[i + w].y));
+            const float2 hi = padd2(make_float2(val[i].z, val[i].w), make_float2(val[i + w].z, val[i + w].w));
+            val[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    }
+    b01 = make_float2(val[0].x, val[0].y);
+    b23 = make_float2(val[0].z, val[0].w);
+}
+
 template <int NV, int FILTER, int TRACE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) __maxnreg__(NV == 1 ? S2_MAXREG : 255)
 render_kernel(const RenderArgs a) {
@@ -334,7 +351,7 @@ render_kernel(const RenderArgs a) {
         // (16-byte stores into this warp's partial row: needs frames % 4 == 0 and an aligned base)
         const bool wide_bus = gbus != nullptr && a.n_voices > 32u && cnt == kChunk && (frames & 3u) == 0u &&
                               (reinterpret_cast<uintptr_t>(gbus) & 15u) == 0u;
-        float4 bsum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float2 b01 = make_float2(0.0f, 0.0f), b23 = make_float2(0.0f, 0.0f);
         if (cnt == kChunk && (gout || wide_bus)) {
             // One pass over the tile, transposed: lane (q, c4) reads 16 bytes of rows 4*i + q.  For banks
             // wider than a warp the same registers also feed the bus: each lane adds its 8*NV rows, then the
@@ -351,25 +368,25 @@ render_kernel(const RenderArgs a) {
                     __stcs(reinterpret_cast<float4*>(dst + tb), val);
                 }
             } else if (all_rows) {
+                float4 val[8 * NV];
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
                     char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
-                    const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
-                    __stcs(reinterpret_cast<float4*>(dst + tb), val);
-                    bsum.x = __fadd_rn(bsum.x, val.x); bsum.y = __fadd_rn(bsum.y, val.y);
-                    bsum.z = __fadd_rn(bsum.z, val.z); bsum.w = __fadd_rn(bsum.w, val.w);
+                    val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                    __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
                 }
+                tree_sum_rows<8 * NV>(val, b01, b23);
             } else {
+                float4 val[8 * NV];
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
-                    const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                    val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
                     if (gout) {
                         char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
-                        if (dst) __stcs(reinterpret_cast<float4*>(dst + tb), val);
+                        if (dst) __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
                     }
-                    bsum.x = __fadd_rn(bsum.x, val.x); bsum.y = __fadd_rn(bsum.y, val.y);
-                    bsum.z = __fadd_rn(bsum.z, val.z); bsum.w = __fadd_rn(bsum.w, val.w);
                 }
+                tree_sum_rows<8 * NV>(val, b01, b23);
             }
         } else if (gout) {
 #pragma unroll
@@ -384,12 +401,10 @@ render_kernel(const RenderArgs a) {
         if (wide_bus) {
 #pragma unroll
             for (int sh = 8; sh <= 16; sh <<= 1) {
-                bsum.x = __fadd_rn(bsum.x, __shfl_xor_sync(0xffffffffu, bsum.x, sh));
-                bsum.y = __fadd_rn(bsum.y, __shfl_xor_sync(0xffffffffu, bsum.y, sh));
-                bsum.z = __fadd_rn(bsum.z, __shfl_xor_sync(0xffffffffu, bsum.z, sh));
-                bsum.w = __fadd_rn(bsum.w, __shfl_xor_sync(0xffffffffu, bsum.w, sh));
+                b01 = padd2(b01, make_float2(__shfl_xor_sync(0xffffffffu, b01.x, sh), __shfl_xor_sync(0xffffffffu, b01.y, sh)));
+                b23 = padd2(b23, make_float2(__shfl_xor_sync(0xffffffffu, b23.x, sh), __shfl_xor_sync(0xffffffffu, b23.y, sh)));
             }
-            if (lane < 8) *reinterpret_cast<float4*>(gbus + t0 + c4) = bsum;
+            if (lane < 8) *reinterpret_cast<float4*>(gbus + t0 + c4) = make_float4(b01.x, b01.y, b23.x, b23.y);
         } else if (gbus) {
             if ((uint32_t)lane < cnt) {
                 float acc;

@@ -577,3 +577,33 @@ def test_full_size_properties_config3():
         st2 = bank.get_state()
     assert bool(torch.equal(out, out2))
     assert st1.tobytes() == st2.tobytes()
+
+
+def test_sweep_variants_config5():
+    """BASELINE config 5 (one GPU's share): the 32 x 32 x 32 cutoff / damping / detune grid of the default
+    patch through the resonant low-pass.  A strided sample of variants against the oracle over the first
+    notes of the render (the moving-cutoff segment, decay, sustain), then at full width: every variant
+    renders exactly as it does alone (independence), and no variant blows up."""
+    T = 4096
+    blocks = [T, T, T, 1024]                       # 13,312 frames: past the 200 ms mod decay and the amp decay
+    v = bankgen.make_sweep_bank(1, 480000)
+    pick = np.arange(5, 32768, 517)                # 64 variants, all three axes move
+    sub = v[pick].copy()
+    ref, _, rst = oracle_bank_render(sub, 1, blocks)
+    got, _, st = gpu_bank_render(sub, 1, blocks, want_bus=False)
+    assert_parity(ref, got, "sweep sample")
+    assert_state_parity(st, rst, 1)
+    # full width, first block: the sample's rows come out bit-identical inside the 32,768-variant bank
+    out = torch.empty((32768, T), device="cuda", dtype=torch.float32)
+    with s2.VoiceBank(v, SR, 1) as bank:
+        bank.set_pipeline(4)
+        bank.render(T, out, T, None)
+        bank.sync()
+    assert bool(torch.isfinite(out).all())
+    rows = out[torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    assert rows.tobytes() == got[:, :T].tobytes()
+    # release at 75 % of a short render: the tail decays to silence for every variant
+    short = bankgen.make_sweep_bank(1, 16384, first_variant=0, n_variants=1024)
+    o, _, _ = gpu_bank_render(short, 1, [16384, 4096 + 2048], want_bus=False)
+    assert np.all(o[:, 12288 + 4800:] == 0.0)      # release 100 ms = 4,800 frames after frame 12,288
+    assert np.all(np.abs(o[:, 12288 + 4700]) > 0.0)

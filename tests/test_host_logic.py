@@ -152,6 +152,36 @@ def test_bankgen_is_counter_based():
     assert list(whole["osc_kind"][:4]) == [s2.OSC_SAW, s2.OSC_SQUARE, s2.OSC_SAW, s2.OSC_SQUARE]
 
 
+def test_sweep_bank_is_the_config5_grid():
+    """BASELINE config 5: 32 cutoffs x 32 dampings x 32 detunes per GPU, MIDI note 48 + 4 * gpu."""
+    cutoff, damping, cents = bankgen.sweep_axes()
+    assert cutoff[0] == np.float32(100.0) and cutoff[-1] == np.float32(12800.0)
+    assert np.allclose(np.diff(np.log2(cutoff.astype(np.float64))), 7.0 / 31.0, atol=1e-6)
+    assert damping[0] == np.float32(0.2) and damping[-1] == np.float32(1.414)
+    assert cents[0] == -50.0 and cents[-1] == 50.0
+    b = bankgen.make_sweep_bank(2, 480000)
+    assert b.shape == (32768,) and np.all(b["active"] == 1)
+    # variant id = (cutoff * 32 + damping) * 32 + detune
+    vid = (7 * 32 + 19) * 32 + 3
+    assert b["lpf_freq_hz"][vid] == cutoff[7] and b["damping"][vid] == damping[19]
+    base = float(np.float32(s2.note_to_pitch(48 + 8)))
+    assert b["pitch_hz"][vid] == np.float32(base * 2.0 ** (cents[3] / 1200.0))
+    assert len(np.unique(b[["pitch_hz", "lpf_freq_hz", "damping"]])) == 32768          # all variants distinct
+    # the mod envelope never opens the cutoff beyond 0.45 * sr (the biquad is unstable above Nyquist)
+    peak = b["lpf_freq_hz"].astype(np.float64) * np.exp2(b["mod_env_to_lpf_freq"].astype(np.float64))
+    assert peak.max() <= 0.45 * 48000 * (1 + 1e-6) and b["mod_env_to_lpf_freq"].min() >= 0.0
+    assert b["release_offset"][0] == 360000
+    # any slice of the grid can be generated on its own (ranks / chunks)
+    part = bankgen.make_sweep_bank(2, 480000, first_variant=1000, n_variants=77)
+    assert part.tobytes() == b[1000:1077].tobytes()
+    # the rest is the default patch
+    d = s2.default_voice(1)[0]
+    for f in ("amp_attack_ms", "amp_decay_ms", "amp_sustain", "amp_release_ms", "mod_decay_ms", "osc_gain", "noise_amt"):
+        assert np.all(b[f] == d[f]), f
+    with pytest.raises(ValueError):
+        bankgen.make_sweep_bank(0, 480000, first_variant=32768, n_variants=1)
+
+
 def test_splitmix64_known_answer():
     # splitmix64 reference stream for seed 0: first output
     assert int(bankgen.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
