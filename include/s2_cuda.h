@@ -149,6 +149,22 @@ int s2_bank_render_bus_host_async(s2_bank* bank, size_t frames, float* d_voice_o
 int s2_bank_set_pipeline(s2_bank* bank, int n_sub);
 int s2_bank_join(s2_bank* bank, void* stream);
 
+/*
+ * Time-split mode for narrow banks (BASELINE config 2: 1,024 voices, 4,096-frame buffers, one-pole filter).
+ * With one voice per lane a bank of a thousand voices leaves most of the GPU idle; enable = 1 lets blocks
+ * whose voices all hold one period and one cutoff (no pitch modulation, mod envelope at rest or unused by
+ * the cutoff) and whose length is a multiple of 1,024 frames render as 32 time segments per voice: the
+ * oscillator phase is stepped alone and exactly (try3/oscillators.rs:377-381, bit-exact as always), the
+ * one-pole filter state (try3/filters.rs:15-34) enters each segment through a prefix scan of the segments'
+ * affine maps.  Output differs from the one-lane-per-voice render only by that scan's reassociation (north
+ * star tolerance), so, unlike the default path, a block is not bit-identical to the same frames rendered as
+ * two half blocks.  Blocks that do not qualify (and every bus / trace request) take the default path;
+ * s2_bank_time_split_blocks counts the blocks that did.  One-pole banks of at most 16,384 voices only;
+ * exclusive with s2_bank_set_pipeline(n_sub > 1).
+ */
+int s2_bank_set_time_split(s2_bank* bank, int enable);
+int s2_bank_time_split_blocks(s2_bank* bank, uint64_t* blocks);
+
 /* Checkpoint / restore / test hook.  Host arrays of n_voices entries; synchronises. */
 int s2_bank_get_state(s2_bank* bank, s2_voice_state* out);
 int s2_bank_set_state(s2_bank* bank, const s2_voice_state* in);

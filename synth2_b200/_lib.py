@@ -59,6 +59,8 @@ SYMBOLS = {
     "s2_bank_sync": (_i, [_vp]),
     "s2_bank_set_pipeline": (_i, [_vp, _i]),
     "s2_bank_join": (_i, [_vp, _vp]),
+    "s2_bank_set_time_split": (_i, [_vp, _i]),
+    "s2_bank_time_split_blocks": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "s2_bank_trace_phase": (_i, [_vp, _sz, _vp, _sz]),
     "s2_launch_count": (C.c_uint64, []),
     "s2_synth_new": (_i, [_i, C.POINTER(_vp)]),

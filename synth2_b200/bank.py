@@ -104,6 +104,17 @@ class VoiceBank:
         """n_sub > 1: render contiguous voice ranges on n_sub internal streams (see include/s2_cuda.h)."""
         check(lib().s2_bank_set_pipeline(self._h, int(n_sub)))
 
+    def set_time_split(self, enable: bool = True):
+        """Narrow one-pole banks: render qualifying blocks as 32 time segments per voice (s2_cuda.h)."""
+        check(lib().s2_bank_set_time_split(self._h, 1 if enable else 0))
+
+    @property
+    def time_split_blocks(self) -> int:
+        """Blocks rendered through the time-split kernels so far."""
+        n = C.c_uint64(0)
+        check(lib().s2_bank_time_split_blocks(self._h, C.byref(n)))
+        return int(n.value)
+
     def join(self, stream=None):
         """Make `stream` (a torch stream, a raw cudaStream_t, or None = default) wait for the bank's work."""
         sp = None if stream is None else C.c_void_p(getattr(stream, "cuda_stream", stream))

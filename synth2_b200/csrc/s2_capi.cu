@@ -116,6 +116,8 @@ struct VoiceBook {           // host mirror of what the device will hold, O(1) p
 // while the sub-banks already render step i+1; with only two buffers step i+2 would have to wait for it,
 // and a reduction that is slow to get SM slots next to the render blocks then stalls the whole pipeline.
 constexpr int kMixBufs = 4;
+constexpr int kTsBufs = 4;                 // the phase pre-pass may run this many blocks ahead of the renders
+constexpr size_t kTsMaxVoices = 16384;     // beyond this a bank fills the machine with one voice per lane
 
 struct s2_bank {
     int device = 0;
@@ -159,6 +161,15 @@ struct s2_bank {
     size_t partials2_cap = 0;
     uint64_t step = 0, table_step = 0;
     int table_pending = -1;               // staging buffer index holding a table not yet applied, or -1
+    // Time-split mode (s2_bank_set_time_split, s2_kernel_ts.cu): narrow one-pole banks render a block as 32
+    // time segments per voice.  The phase pre-pass runs on its own stream, ahead of the renders.
+    bool ts_enabled = false;
+    bool ts_main_dirty = true;            // b->stream carries state writes the pre-pass stream has not seen
+    cudaStream_t ts = nullptr;
+    float* d_seg_phase[kTsBufs] = {};     // [n_voices][32] segment-start phases of block p
+    cudaEvent_t ev_k1[kTsBufs] = {}, ev_k2[kTsBufs] = {}, ev_main = nullptr;
+    uint64_t ts_step = 0, ts_blocks = 0;  // ts_blocks: blocks rendered through the time-split kernels
+    std::vector<s2_voice_desc> descs;     // host copy of the voice descriptions (banks <= kTsMaxVoices only)
     uint64_t total_frames = 0;
     uint64_t max_offset = 0;     // upper bound of any active voice's frame offset
     size_t n_sine = 0;
@@ -178,6 +189,7 @@ int bank_drain(s2_bank* b) {
     for (int k = 0; k < b->n_sub && b->n_sub > 1; k++) CUDA_TRY(cudaStreamSynchronize(b->sub[k]));
     if (b->mix) CUDA_TRY(cudaStreamSynchronize(b->mix));
     if (b->upload) CUDA_TRY(cudaStreamSynchronize(b->upload));
+    if (b->ts) CUDA_TRY(cudaStreamSynchronize(b->ts));
     return S2_OK;
 }
 
@@ -258,6 +270,75 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
     return S2_OK;
 }
 
+// units.rs:44-53 in host f32 arithmetic (IEEE, no contraction: same bits as the device's make_env)
+float host_ms_as_samples(float ms, float sr) { return sr * (ms / 1000.0f); }
+
+// May this block go through the time-split kernels?  Every active voice must keep one period and one
+// cutoff for the whole block: no pitch modulation, and the mod envelope either unused by the cutoff or
+// resting (sustain / end) until the block ends.  Conservative: anything unsure renders the general way.
+bool ts_block_eligible(const s2_bank* b, size_t frames, const float* d_voice_out, const float* d_bus_out) {
+    if (!b->ts_enabled || b->filter_kind != S2_FILTER_ONE_POLE || !d_voice_out || d_bus_out) return false;
+    if (frames < 1024 || (frames & 1023u) != 0 || frames > (1u << 24)) return false;   // 32 segments of whole chunks
+    const float sr = (float)b->sample_rate;
+    for (size_t i = 0; i < b->n_voices; i++) {
+        if (!b->book[i].active) continue;
+        const s2_voice_desc& d = b->descs[i];
+        if (d.mod_env_to_osc_freq != 0.0f) return false;
+        const uint64_t n0 = current_offset(b, i);
+        if (n0 + frames > (1ull << 24)) return false;
+        const float P = sr / d.pitch_hz;
+        const float step = 1.0f / P;
+        if (!(step < 1.0f && P > 1.0f)) return false;
+        if (d.mod_env_to_lpf_freq != 0.0f) {
+            const float A = host_ms_as_samples(d.mod_attack_ms, sr), D = host_ms_as_samples(d.mod_decay_ms, sr);
+            const float R = host_ms_as_samples(d.mod_release_ms, sr);
+            const float AD = A + D;
+            const float Rs = fmaxf((float)d.release_offset, AD);
+            const float E = Rs + R;
+            const float x0 = (float)(uint32_t)n0, x1 = (float)(uint32_t)(n0 + frames - 1);
+            const bool rest_sustain = x0 >= A && x0 >= AD && x1 < Rs;     // stage 2 from first to last frame
+            const bool rest_end = x0 >= A && x0 >= AD && x0 >= Rs && x0 >= E;
+            if (!(rest_sustain || rest_end)) return false;
+        }
+    }
+    return true;
+}
+
+int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride) {
+    const int p = (int)(b->ts_step % (uint64_t)kTsBufs);
+    s2::RenderArgs a;
+    a.params = b->d_params;
+    a.state = b->d_state;
+    a.n_voices = (uint32_t)b->n_voices;
+    a.slot_begin = 0;
+    a.slot_end = (uint32_t)b->n_voices;
+    a.vpad = (uint32_t)b->vpad;
+    a.sample_rate = (float)b->sample_rate;
+    a.frames = (uint32_t)frames;
+    a.voice_out = d_voice_out;
+    a.row_stride = row_stride;
+    a.bus_partials = nullptr;
+    a.has_sine = b->n_sine ? 1u : 0u;
+    if (b->ts_main_dirty) {
+        // the pre-pass reads the carried phase: order it after whatever the bank's stream wrote
+        CUDA_TRY(cudaEventRecord(b->ev_main, b->stream));
+        CUDA_TRY(cudaStreamWaitEvent(b->ts, b->ev_main, 0));
+        b->ts_main_dirty = false;
+    }
+    if (b->ts_step >= (uint64_t)kTsBufs) CUDA_TRY(cudaStreamWaitEvent(b->ts, b->ev_k2[p], 0));   // seg_phase[p] is free again
+    CUDA_TRY(s2::launch_ts_phase(a, b->d_seg_phase[p], b->ts));
+    CUDA_TRY(cudaEventRecord(b->ev_k1[p], b->ts));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_k1[p], 0));
+    CUDA_TRY(s2::launch_ts_render(a, b->d_seg_phase[p], b->stream));
+    CUDA_TRY(cudaEventRecord(b->ev_k2[p], b->stream));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    b->ts_step++;
+    b->ts_blocks++;
+    b->total_frames += frames;
+    b->max_offset += frames;
+    return S2_OK;
+}
+
 int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out,
                      int trace) {
     if (!b) return fail(S2_ERR_INVALID, "null bank");
@@ -270,6 +351,9 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     if (b->max_offset + frames > 0xFFFFFFFFull)
         return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
     CUDA_TRY(cudaSetDevice(b->device));
+    if (trace == s2::TRACE_NONE && ts_block_eligible(b, frames, d_voice_out, d_bus_out))
+        return bank_render_time_split(b, frames, d_voice_out, row_stride);
+    b->ts_main_dirty = true;      // the general kernels below move the carried phase on the bank's stream
     if (b->n_sub > 1 && trace == s2::TRACE_NONE) return bank_render_pipelined(b, frames, d_voice_out, row_stride, d_bus_out);
     if (b->n_sub > 1) { int rc = bank_drain(b); if (rc) return rc; }
 
@@ -390,6 +474,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->n_voices = n_voices;
     b->vpad = (n_voices + 63) & ~(size_t)63;
     b->book.resize(n_voices);
+    if (n_voices <= kTsMaxVoices) b->descs.assign(voices, voices + n_voices);
     b->nv = 1;   // 2 = two voices per lane with packed f32x2 math: fewer issue slots but half the warps; measured no faster
     b->pc = false;   // measured slower than the one-warp kernel (profiles/r1_notes.md); S2_PC=1 selects it
     if (const char* f = getenv("S2_PC")) b->pc = f[0] == '1';   // test hook
@@ -463,6 +548,13 @@ void s2_bank_destroy(s2_bank* b) {
         cudaFree(b->d_partials2[i]);
     }
     if (b->ev_tail) cudaEventDestroy(b->ev_tail);
+    if (b->ts) { cudaStreamSynchronize(b->ts); cudaStreamDestroy(b->ts); }
+    for (int i = 0; i < kTsBufs; i++) {
+        if (b->ev_k1[i]) cudaEventDestroy(b->ev_k1[i]);
+        if (b->ev_k2[i]) cudaEventDestroy(b->ev_k2[i]);
+        cudaFree(b->d_seg_phase[i]);
+    }
+    if (b->ev_main) cudaEventDestroy(b->ev_main);
     delete b;
 }
 
@@ -491,6 +583,7 @@ int s2_bank_set_voice(s2_bank* b, size_t index, const s2_voice_desc* voice) {
     if (b->book[index].osc_kind == S2_OSC_SINE) b->n_sine--;
     if (voice->osc_kind == S2_OSC_SINE) b->n_sine++;
     b->book[index] = {voice->frame_offset, b->total_frames, voice->active ? 1u : 0u, voice->osc_kind};
+    if (!b->descs.empty()) b->descs[index] = *voice;
     if (voice->active && voice->frame_offset > b->max_offset) b->max_offset = voice->frame_offset;
     return S2_OK;
 }
@@ -504,12 +597,14 @@ int s2_bank_release_voice(s2_bank* b, size_t index) {
     CUDA_TRY(cudaMemcpyAsync(b->d_params + (size_t)s2::P_RELEASE * b->vpad + b->slot_of_voice[index], &rel,
                              sizeof rel, cudaMemcpyHostToDevice, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (!b->descs.empty()) b->descs[index].release_offset = rel;
     return S2_OK;
 }
 
 int s2_bank_set_releases(s2_bank* b, const uint32_t* h_release) {
     if (!b || !h_release) return fail(S2_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->device));
+    for (size_t i = 0; i < b->descs.size(); i++) b->descs[i].release_offset = h_release[i];
     if (b->n_sub > 1) {
         // stage the table on the mix stream; every sub-bank applies it to its own slots right before its
         // next render (bank_render_pipelined), so no sub-bank waits for another
@@ -633,6 +728,7 @@ int s2_bank_sync(s2_bank* b) {
 int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
     if (!b) return fail(S2_ERR_INVALID, "null bank");
     if (n_sub < 1 || n_sub > 8) return fail(S2_ERR_INVALID, "n_sub must be in [1, 8]");
+    if (n_sub > 1 && b->ts_enabled) return fail(S2_ERR_INVALID, "time-split and pipelined voice ranges are exclusive");
     CUDA_TRY(cudaSetDevice(b->device));
     { int rc = s2_bank_sync(b); if (rc) return rc; }
     if (n_sub > 1) {
@@ -665,6 +761,35 @@ int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
     b->step = 0;
     b->table_step = 0;
     b->table_pending = -1;
+    return S2_OK;
+}
+
+int s2_bank_set_time_split(s2_bank* b, int enable) {
+    if (!b) return fail(S2_ERR_INVALID, "null bank");
+    CUDA_TRY(cudaSetDevice(b->device));
+    { int rc = s2_bank_sync(b); if (rc) return rc; }
+    if (!enable) { b->ts_enabled = false; return S2_OK; }
+    if (b->filter_kind != S2_FILTER_ONE_POLE)
+        return fail(S2_ERR_INVALID, "time-split rendering composes the one-pole filter's affine state map; this bank uses the biquad");
+    if (b->n_voices > kTsMaxVoices)
+        return fail(S2_ERR_INVALID, "time-split rendering is for narrow banks (<= %zu voices)", kTsMaxVoices);
+    if (b->n_sub > 1) return fail(S2_ERR_INVALID, "time-split and pipelined voice ranges are exclusive");
+    if (!b->ts) CUDA_TRY(cudaStreamCreateWithFlags(&b->ts, cudaStreamNonBlocking));
+    for (int i = 0; i < kTsBufs; i++) {
+        if (!b->d_seg_phase[i]) CUDA_TRY(cudaMalloc(&b->d_seg_phase[i], b->n_voices * 32 * sizeof(float)));
+        if (!b->ev_k1[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_k1[i], cudaEventDisableTiming));
+        if (!b->ev_k2[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_k2[i], cudaEventDisableTiming));
+    }
+    if (!b->ev_main) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming));
+    b->ts_enabled = true;
+    b->ts_main_dirty = true;
+    b->ts_step = 0;
+    return S2_OK;
+}
+
+int s2_bank_time_split_blocks(s2_bank* b, uint64_t* blocks) {
+    if (!b || !blocks) return fail(S2_ERR_INVALID, "null argument");
+    *blocks = b->ts_blocks;
     return S2_OK;
 }
 

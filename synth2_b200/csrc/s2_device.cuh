@@ -119,6 +119,15 @@ __device__ __forceinline__ float seg_eval(const SegEnv& s, float x) {
     return __fadd_rn(__fmul_rn(s.es, __fadd_rn(x, s.nex0)), s.ey0);
 }
 
+// fmod(t, 1) for t in [0, 2) (the fast paths: 0 <= phase < 1, 0 <= 1/P < 1): t - 1 is exact there, and as
+// unsigned integers the bits of a negative t - 1 exceed those of any t < 1 while a non-negative t - 1 lies
+// below t >= 1, so the wrap is one integer min.  No predicate: FSETP/ISETP -> FSEL or a predicated FADD costs
+// 14 cycles of latency on this part against 6.75 for VIMNMX (tools/ubench/phase_chain.cu: 22.9 -> 14.75 cycles
+// per step of the recurrence, same bits).
+__device__ __forceinline__ float wrap_unit(float t) {
+    return __uint_as_float(min(__float_as_uint(__fadd_rn(t, -1.0f)), __float_as_uint(t)));
+}
+
 // math.rs:11-19 with feature "fma"
 __device__ __forceinline__ float line_fma(float rise, float run, float x, float y0) {
     return __fmaf_rn(__fdiv_rn(rise, run), x, y0);
@@ -256,7 +265,7 @@ __device__ __forceinline__ float osc_step(uint32_t kind, const OscC& o, float& p
     }
     const float t = __fadd_rn(ph, o.d);
     if (LITERAL) ph = fmodf(t, 1.0f);
-    else ph = t >= 1.0f ? __fadd_rn(t, -1.0f) : t;
+    else ph = wrap_unit(t);
     return y;
 }
 
@@ -520,9 +529,9 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             // ---- phase recurrence, two frames (try3/oscillators.rs:377-381; see osc_step)
             const float pa = ph;
             const float ta = __fadd_rn(pa, F.d);
-            const float pb = ta >= 1.0f ? __fadd_rn(ta, -1.0f) : ta;
+            const float pb = wrap_unit(ta);
             const float tb = __fadd_rn(pb, F.d);
-            ph = tb >= 1.0f ? __fadd_rn(tb, -1.0f) : tb;
+            ph = wrap_unit(tb);
             const float2 ph2 = make_float2(pa, pb);
             // ---- waveform: x = period.mul_add(phase, 0); `% period` is a no-op
             const float2 x2 = pmul2(P2, ph2);

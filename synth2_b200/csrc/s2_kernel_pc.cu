@@ -98,9 +98,9 @@ __device__ __forceinline__ void produce_chunk(const OscC& o, float gain, float n
                 // phase recurrence, two frames (try3/oscillators.rs:377-381; see osc_step)
                 const float pa = ph;
                 const float ta = __fadd_rn(pa, o.d);
-                const float pb = ta >= 1.0f ? __fadd_rn(ta, -1.0f) : ta;
+                const float pb = wrap_unit(ta);
                 const float tb = __fadd_rn(pb, o.d);
-                ph = tb >= 1.0f ? __fadd_rn(tb, -1.0f) : tb;
+                ph = wrap_unit(tb);
                 const float2 x2 = pmul2(P2, make_float2(pa, pb));
                 float2 osc2;
                 if (KIND == 1) {

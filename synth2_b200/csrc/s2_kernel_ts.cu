@@ -1,0 +1,192 @@
+// s2_kernel_ts.cu — time-split rendering for narrow banks (BASELINE config 2: 1,024 voices x 4,096 frames).
+//
+// A bank of a thousand voices is 32 warps: with one voice per lane the whole GPU waits on 32 dependent
+// instruction streams (131 us per 16 MiB block, 2 % of the HBM roofline).  Voices are independent but so,
+// almost, are the time segments of one voice: everything in a frame is a closed form of the frame offset
+// except the two recurrences —
+//
+//   * the oscillator phase, phase' = (phase + 1/P) % 1 in binary32 (try3/oscillators.rs:377-381), whose
+//     rounding cannot be reassociated if it is to stay bit-exact: it is stepped sequentially, but ALONE
+//     (3 dependent instructions per frame instead of the whole frame), by `ts_phase_kernel`, which records
+//     the phase at the start of each of the block's 32 time segments;
+//   * the one-pole low-pass y = fma(1-k, u, k*y') (try3/filters.rs:15-34), an affine map of its state:
+//     segment s as a whole is y_out = K*y_in + Y_s with K = k^L and Y_s its zero-state response, and the 32
+//     segment maps of a voice compose by a warp-shuffle prefix scan (the "block-wide parallel prefix scan
+//     over the associative affine state-transition operator" of the north star).
+//
+// `ts_render_kernel`: one warp per voice, lane s = frames [s*L, (s+1)*L) of the block (L = frames / 32).
+// Sweep 1 renders the segment from a zero filter state to get Y_s; the scan gives every lane its true start
+// state; sweep 2 renders the segment again from that state with the reference's own recurrence and writes
+// it out through the transposed smem tile (128-byte runs per row, like the wide-bank kernel).  The second
+// sweep costs nothing that matters: the shape is latency-bound and the machine is otherwise idle.
+//
+// Parity: phase bit-exact (same recurrence, same order); output within the north-star tolerance (the start
+// state of segments 1..31 carries the scan's reassociation error, ~1 ulp of the state, and decays as k^n).
+// Used only when every voice of the block has a constant period and cutoff (host check in s2_capi.cu);
+// anything else renders through the wide-bank kernel.
+#include "s2_device.cuh"
+
+namespace s2 {
+namespace {
+
+constexpr int kSegs = 32;                 // time segments per block = lanes per warp
+
+// K1: lane = voice slot.  phase recurrence only, 8 frames per trip.
+__global__ void __launch_bounds__(32) ts_phase_kernel(const RenderArgs a, float* __restrict__ seg_phase) {
+    const uint32_t slot = blockIdx.x * 32u + threadIdx.x;
+    if (slot >= a.n_voices) return;
+    const uint32_t vp = a.vpad;
+    const float* __restrict__ P = a.params + slot;
+    if (__float_as_uint(P[P_ACTIVE * vp]) == 0u) return;
+    float* __restrict__ S = a.state + slot;
+    OscC oc;
+    make_osc(oc, P[P_PITCH * vp], a.sample_rate);            // mod_env_to_osc_freq == 0: fo == pitch exactly
+    const float d = oc.d;
+    float ph = __float_as_uint(S[S_HAS_PHASE * vp]) != 0u ? S[S_PHASE * vp] : 0.0f;      // process.rs:316
+    const uint32_t L = a.frames / kSegs;
+    float* __restrict__ out = seg_phase + (size_t)slot * kSegs;
+    for (int s = 0; s < kSegs; s++) {
+        out[s] = ph;
+#pragma unroll 1
+        for (uint32_t j = 0; j < L; j += 8u) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                ph = wrap_unit(__fadd_rn(ph, d));            // fmod(phase + d, 1), s2_device.cuh
+            }
+        }
+    }
+    S[S_PHASE * vp] = ph;
+    S[S_HAS_PHASE * vp] = __uint_as_float(1u);
+}
+
+template <int KIND, bool GCONST>
+__device__ __forceinline__ void ts_chunk(FastV<1>& F, const EnvP* amp, uint32_t kind, uint32_t rot, uint32_t n,
+                                         float* row, const float* sintab) {
+    chunk_fast_tp<0, KIND, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab);
+}
+
+template <bool GCONST>
+__device__ __forceinline__ void ts_chunk_kind(FastV<1>& F, const EnvP* amp, uint32_t kind, uint32_t rot, uint32_t n,
+                                              float* row, const float* sintab) {
+    switch (kind) {                       // warp-uniform: a warp is one voice
+    case 0: ts_chunk<0, GCONST>(F, amp, kind, rot, n, row, sintab); break;
+    case 1: ts_chunk<1, GCONST>(F, amp, kind, rot, n, row, sintab); break;
+    case 2: ts_chunk<2, GCONST>(F, amp, kind, rot, n, row, sintab); break;
+    default: ts_chunk<3, GCONST>(F, amp, kind, rot, n, row, sintab); break;
+    }
+}
+
+// K2: one warp per voice slot; lane = time segment.
+__global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const float* __restrict__ seg_phase) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;                                      // [32 segments][kTileStride]
+    float* sintab = smem + 32 * kTileStride;
+    const int lane = threadIdx.x;
+    const uint32_t slot = blockIdx.x;
+    const uint32_t vp = a.vpad;
+    const float sr = a.sample_rate;
+    const float* __restrict__ P = a.params + slot;           // warp-uniform loads
+    const uint32_t frames = a.frames;
+    const uint32_t L = frames / kSegs;
+    const uint32_t orow = __float_as_uint(P[P_ROW * vp]);
+    float* __restrict__ gout = a.voice_out + (size_t)orow * a.row_stride;
+    const int q = lane >> 3, c4 = (lane & 7) * 4;
+
+    if (__float_as_uint(P[P_ACTIVE * vp]) == 0u) {
+        // inactive voices render silence (their state does not move)
+        for (uint32_t t = (uint32_t)lane * 4u; t < frames; t += 128u)
+            __stcs(reinterpret_cast<float4*>(gout + t), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        return;
+    }
+    const uint32_t kind = __float_as_uint(P[P_KIND * vp]);
+    if (kind == 3u) {
+        for (int i = lane; i < 1024; i += 32) sintab[i] = __uint_as_float(d_sin_bits[i]);
+    }
+    const uint32_t seed = __float_as_uint(P[P_SEED * vp]);
+    const uint32_t rot = (seed << 5) | (seed >> 27);
+    const uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
+    EnvP A, M;
+    make_env(A, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
+    make_env(M, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
+    float* __restrict__ S = a.state + slot;
+    const uint32_t n0 = __float_as_uint(S[S_OFFSET * vp]);
+    const float last = S[S_LAST * vp];
+
+    // constants of the block: the host admitted this voice because its period and cutoff do not move
+    const float amt_lpf = P[P_AMT_LPF * vp];
+    const float m = (amt_lpf != 0.0f && env_stage(M, __uint2float_rn(n0)) == 2) ? M.S : 0.0f;
+    const float fl = modulate_freq(P[P_LPF * vp], m, amt_lpf);
+    OscC oc;
+    FiltC fc;
+    make_osc(oc, P[P_PITCH * vp], sr);
+    make_filt<0>(fc, fl, P[P_DAMP * vp], sr);
+
+    FastV<1> F;
+    F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
+    F.gain = P[P_GAIN * vp]; F.namt = P[P_NOISE * vp];
+    F.c0 = fc.c0; F.c1 = fc.c1; F.c2 = fc.c2;
+    F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f;
+    F.x1 = 0.0f; F.x2 = 0.0f; F.y2 = 0.0f;
+    const float ph0 = seg_phase[(size_t)slot * kSegs + lane];
+    const uint32_t nl = n0 + (uint32_t)lane * L;             // this lane's first frame offset
+    float* row = tile + lane * kTileStride;
+    __syncwarp();
+
+    // ---- sweep 1: zero-state response of the segment (gain and output are irrelevant)
+    F.ph = ph0;
+    F.y1 = 0.0f;
+    for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<true>(F, &A, kind, rot, nl + c, row, sintab);
+    const float Yseg = F.y1;
+
+    // ---- the segment maps y -> K*y + Y compose left to right: inclusive Hillis-Steele scan over the lanes
+    float Kc = (float)exp((double)L * log((double)fc.c0));   // k^L (one value per voice)
+    float Yc = Yseg;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float Kp = __shfl_up_sync(0xffffffffu, Kc, off);
+        const float Yp = __shfl_up_sync(0xffffffffu, Yc, off);
+        if (lane >= off) {                                    // (Kp, Yp) happens first, then (Kc, Yc)
+            Yc = __fmaf_rn(Kc, Yp, Yc);
+            Kc = __fmul_rn(Kc, Kp);
+        }
+    }
+    const float end_state = __fmaf_rn(Kc, last, Yc);          // state after this lane's segment
+    float y_in = __shfl_up_sync(0xffffffffu, end_state, 1);
+    if (lane == 0) y_in = last;
+
+    // ---- sweep 2: the reference recurrence from the true start state, written out
+    F.ph = ph0;
+    F.y1 = y_in;
+    for (uint32_t c = 0; c < L; c += kChunk) {
+        ts_chunk_kind<false>(F, &A, kind, rot, nl + c, row, sintab);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + q;                          // tile row = segment r
+            const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+            __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
+        }
+        __syncwarp();
+    }
+    if (lane == 31) {
+        S[S_LAST * vp] = F.y1;
+        S[S_OFFSET * vp] = __uint_as_float(n0 + frames);      // n0 + frames <= 2^24 (host check)
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t stream) {
+    if (a.n_voices == 0) return cudaSuccess;
+    ts_phase_kernel<<<(a.n_voices + 31u) / 32u, 32, 0, stream>>>(a, seg_phase);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ts_render(const RenderArgs& a, const float* seg_phase, cudaStream_t stream) {
+    if (a.n_voices == 0) return cudaSuccess;
+    const size_t smem = (32 * kTileStride + 1024) * sizeof(float);
+    ts_render_kernel<<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    return cudaGetLastError();
+}
+
+}  // namespace s2

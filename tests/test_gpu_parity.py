@@ -607,3 +607,90 @@ def test_sweep_variants_config5():
     o, _, _ = gpu_bank_render(short, 1, [16384, 4096 + 2048], want_bus=False)
     assert np.all(o[:, 12288 + 4800:] == 0.0)      # release 100 ms = 4,800 frames after frame 12,288
     assert np.all(np.abs(o[:, 12288 + 4700]) > 0.0)
+
+
+# ------------------------------------------------------------------------------ time-split (narrow banks)
+
+def _render_blocks(voices, filter_kind, blocks, time_split, kinds_stride=None):
+    V = voices.shape[0]
+    outs = []
+    with s2.VoiceBank(voices, SR, filter_kind) as bank:
+        if time_split:
+            bank.set_time_split(True)
+        for fr in blocks:
+            vo = torch.full((V, fr), float("nan"), device="cuda", dtype=torch.float32)
+            bank.render(fr, vo, fr, None)
+            bank.sync()
+            outs.append(vo.cpu().numpy())
+        st = bank.get_state()
+        n_ts = bank.time_split_blocks
+    return np.concatenate(outs, axis=1), st, n_ts
+
+
+def test_time_split_config2_against_oracle():
+    """BASELINE config 2 through the time-split kernels: 1,024 saw/square voices + one-pole low-pass,
+    4,096-frame buffers, carried state.  The first blocks (200 ms mod-envelope decay on half the voices)
+    do not qualify and take the default path; the rest render as 32 segments per voice.  Phase bit-exact,
+    output within the north-star tolerance, against the oracle and against the default path."""
+    V, T, N = 1024, 4096, 6
+    v = bank_for(0, V, 400000)
+    ref, _, rst = oracle_bank_render(v, 0, [T] * N)
+    got, st, n_ts = _render_blocks(v, 0, [T] * N, True)
+    assert n_ts == N - 3                      # blocks 0-2 hold the 9,600-frame mod decay
+    assert_parity(ref, got, "config 2 time-split vs oracle")
+    assert_state_parity(st, rst, 0)
+    plain, st0, n0 = _render_blocks(v, 0, [T] * N, False)
+    assert n0 == 0
+    assert st["phase"].tobytes() == st0["phase"].tobytes()
+    assert np.array_equal(st["frame_offset"], st0["frame_offset"])
+    assert_parity(plain, got, "config 2 time-split vs default path")
+
+
+def test_time_split_envelopes_kinds_and_fallbacks():
+    """Every block qualifies when the cutoff ignores the mod envelope: attack / decay / release ramps then
+    cross segment boundaries inside a block, and the release lands mid-block.  All four oscillators, noise
+    amount, inactive voices; block lengths that are not a multiple of 1,024 fall back to the default path."""
+    V = 160
+    v = bank_for(0, V, 20480, kinds=(s2.OSC_SAW, s2.OSC_SQUARE, s2.OSC_TRIANGLE, s2.OSC_SINE),
+                 mod_to_lpf_choices=(0.0,))
+    v["noise_amt"][::3] = 0.25
+    v["osc_gain"][::5] = 0.5
+    v["active"][7::31] = 0
+    v["release_offset"][::2] = 9000           # not a multiple of 16: note-offs land anywhere
+    blocks = [4096, 2048, 1024, 4096, 1000, 3096, 8192]
+    ref, _, rst = oracle_bank_render(v, 0, blocks)
+    got, st, n_ts = _render_blocks(v, 0, blocks, True)
+    assert n_ts == 5                          # 1000 and 3096 are not multiples of 1,024
+    assert_parity(ref, got, "time-split envelopes/kinds")
+    assert_state_parity(st, rst, 0)
+    assert np.all(got[v["active"] == 0] == 0.0)
+
+
+def test_time_split_follows_note_offs_and_mod_release():
+    """Voices whose cutoff follows the mod envelope qualify only while that envelope rests: a note-off that
+    starts a mod release inside a block sends that block to the default path, later blocks qualify again."""
+    V, T = 64, 2048
+    v = bank_for(0, V, 10 * T)                # release at 15,360 = block 7.5
+    v["mod_release_ms"] = 20.0
+    v["mod_sustain"] = 0.6
+    ref, _, rst = oracle_bank_render(v, 0, [T] * 10)
+    got, st, n_ts = _render_blocks(v, 0, [T] * 10, True)
+    # blocks 0-4 hold the 9,600-frame decay, block 7 the release start (and its 960-frame ramp)
+    assert n_ts == 10 - 5 - 1
+    assert_parity(ref, got, "time-split mod release")
+    assert_state_parity(st, rst, 0)
+
+
+def test_time_split_argument_errors():
+    v = bank_for(1, 64, 48000)
+    with s2.VoiceBank(v, SR, 1) as bank:
+        with pytest.raises(s2.S2Error):
+            bank.set_time_split(True)          # biquad bank
+    with s2.VoiceBank(bank_for(0, 64, 48000), SR, 0) as bank:
+        bank.set_time_split(True)
+        with pytest.raises(s2.S2Error):
+            bank.set_pipeline(4)
+        bank.set_time_split(False)
+        bank.set_pipeline(2)
+        with pytest.raises(s2.S2Error):
+            bank.set_time_split(True)

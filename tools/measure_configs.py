@@ -50,17 +50,26 @@ def report(name, voices, frames, seconds, **extra):
 
 def config2(stream):
     V, T, blocks = 1024, 4096, 256
-    voices = bankgen.make_bank(V, blocks * T)
-    bank = s2.VoiceBank(voices, SR, s2.FILTER_ONE_POLE, device=0, stream=stream)
-    ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
-    st = bank.get_state()
-    for i in range(8):
-        bank.render(T, ring[i & 15], T, None)
-    bank.set_state(st)
-    sec = timed(stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
-    report("2: 1,024 saw/square + one-pole, 4,096-frame buffers", V, blocks * T, sec, blocks=blocks,
-           us_per_block=sec / blocks * 1e6)
-    bank.close()
+    voices = bankgen.make_bank(V, 4 * blocks * T)
+    for time_split in (False, True):
+        bank = s2.VoiceBank(voices, SR, s2.FILTER_ONE_POLE, device=0, stream=stream)
+        if time_split:
+            bank.set_time_split(True)
+        ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
+        st = bank.get_state()
+        for i in range(8):
+            bank.render(T, ring[i & 15], T, None)
+        bank.set_state(st)
+        n0 = bank.time_split_blocks
+        sec = timed(stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
+        name = "2: 1,024 saw/square + one-pole, 4,096-frame buffers" + (", time-split" if time_split else ", one voice per lane")
+        report(name + ", from note-on", V, blocks * T, sec, blocks=blocks, us_per_block=sec / blocks * 1e6,
+               time_split_blocks=bank.time_split_blocks - n0)
+        n0 = bank.time_split_blocks
+        sec = timed(stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
+        report(name + ", next 256 blocks (sustain)", V, blocks * T, sec, blocks=blocks, us_per_block=sec / blocks * 1e6,
+               time_split_blocks=bank.time_split_blocks - n0)
+        bank.close()
 
 
 def config4(stream):
