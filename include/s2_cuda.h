@@ -186,6 +186,43 @@ int s2_synth_note_off(s2_synth* synth, uint8_t note);                 /* synth.r
 /* Synth::sample(&mut self, buffer: &mut [f32], sample_rate) synth.rs:154-169: overwrites
    `frames` floats of HOST memory with the mono mix of the 8 voices. */
 int s2_synth_sample(s2_synth* synth, float* h_buffer, size_t frames, uint32_t sample_rate);
+/* ---- Patch description, note events, offline render ----
+ *
+ * The reference's Synth plays one hard-wired patch (`Synth.config` is private and always
+ * `default_config()`, synth.rs:10,56,125-152) and is driven 16 frames at a time by `s2_bin`
+ * (main.rs:138-147), which applies the MIDI messages that arrived since the previous chunk and then calls
+ * `Synth::sample`.  These entries are that loop as one call, plus the patch the `.synth2` file was meant to
+ * carry (example.synth2 is an empty `synth mySynth { }`).  Format: synth2_b200/csrc/s2_patch.cpp.
+ */
+typedef struct s2_patch {
+    s2_voice_desc voice;     /* static_config::Layer as a voice template: pitch/offsets/active are ignored */
+    uint32_t filter_kind;    /* S2_FILTER_ONE_POLE (the reference's live path) or S2_FILTER_BIQUAD_LP */
+    char name[60];           /* `synth NAME { ... }` */
+} s2_patch;                  /* 144 bytes */
+
+typedef struct s2_note_event {
+    uint64_t frame;          /* arrival time in frames from the start of the render */
+    uint8_t note;            /* synth::Note */
+    uint8_t on;              /* 1 = note_on, 0 = note_off */
+    uint8_t reserved[2];
+    float velocity;          /* synth::Velocity (Unipolar<1>); stored, never read by the DSP (synth.rs:26) */
+} s2_note_event;             /* 16 bytes */
+
+void s2_default_patch(s2_patch* out);     /* Synth::default_config(), one-pole filter, empty name */
+/* Parses `.synth2` text.  `events` may be NULL (then the score block is only counted); times given in
+   s / ms are converted with `sample_rate`.  Errors carry the line number in s2_last_error(). */
+int s2_patch_parse(const char* text, uint32_t sample_rate, s2_patch* out, s2_note_event* events,
+                   size_t events_cap, size_t* n_events);
+/* Notes started after this call play `patch` (notes already sounding keep theirs).  A change of filter kind
+   rebuilds the voice bank and is only allowed while no voice is sounding. */
+int s2_synth_set_patch(s2_synth* synth, const s2_patch* patch);
+/* Renders `frames` frames of mono mix into HOST memory, applying each event before the first 16-frame chunk
+   that starts at or after its arrival time (the s2_bin loop: main.rs:138-147; a 2048-frame player buffer is
+   128 such chunks).  Events must be in time order; events at or beyond `frames` are not applied.  The mix is
+   rendered into a device buffer, one launch per stretch between events, and copied back once. */
+int s2_synth_render_score(s2_synth* synth, const s2_note_event* events, size_t n_events, uint32_t sample_rate,
+                          float* h_buffer, size_t frames);
+
 /* test hook: slot contents; returns 1 if the slot has a current_frame_offset, 0 if free */
 int s2_synth_voice_info(s2_synth* synth, int slot, uint8_t* note, uint32_t* current_offset,
                         uint32_t* release_offset, s2_voice_state* state);

@@ -6,17 +6,19 @@ the host-side mirror of the reference interface:
     Synth        synth::Synth          s2_lib/src/try3/synth.rs:9-203
     VoiceBank    the batched form of   process::process_layer_buf_simd (process.rs:14-49)
     bankgen      synthetic voice banks of BASELINE.json's shapes
+    patch        `.synth2` patch + score files (example.synth2); `python -m synth2_b200.render` renders one
 
 Importing the package does not need a GPU; creating a Synth / VoiceBank does, and fails loudly
 without one (no CPU or PyTorch fallback exists).
 """
-from ._lib import (FILTER_BIQUAD_LP, FILTER_ONE_POLE, NO_RELEASE, OSC_SAW, OSC_SINE, OSC_SQUARE,
-                   OSC_TRIANGLE, VOICE_DESC, VOICE_STATE, S2Error, lib)
+from ._lib import (FILTER_BIQUAD_LP, FILTER_ONE_POLE, NO_RELEASE, NOTE_EVENT, OSC_SAW, OSC_SINE, OSC_SQUARE,
+                   OSC_TRIANGLE, PATCH, VOICE_DESC, VOICE_STATE, S2Error, lib)
+from . import patch
 from .bank import VoiceBank, default_voice, note_to_pitch
 from .synth import FrameOffset, Note, Synth, Velocity
 
 __all__ = [
     "Synth", "Note", "Velocity", "FrameOffset", "VoiceBank", "default_voice", "note_to_pitch",
-    "VOICE_DESC", "VOICE_STATE", "S2Error", "lib", "NO_RELEASE",
+    "VOICE_DESC", "VOICE_STATE", "PATCH", "NOTE_EVENT", "patch", "S2Error", "lib", "NO_RELEASE",
     "OSC_SQUARE", "OSC_SAW", "OSC_TRIANGLE", "OSC_SINE", "FILTER_ONE_POLE", "FILTER_BIQUAD_LP",
 ]

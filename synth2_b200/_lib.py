@@ -35,7 +35,11 @@ VOICE_STATE = np.dtype([
     ("phase", "<f4"), ("has_phase", "<u4"), ("frame_offset", "<u4"), ("lpf_last", "<f4"),
     ("x1", "<f4"), ("x2", "<f4"), ("y1", "<f4"), ("y2", "<f4"),
 ])
+# struct s2_patch (144 bytes) / s2_note_event (16 bytes)
+PATCH = np.dtype([("voice", VOICE_DESC), ("filter_kind", "<u4"), ("name", "S60")])
+NOTE_EVENT = np.dtype([("frame", "<u8"), ("note", "u1"), ("on", "u1"), ("reserved", "u1", (2,)), ("velocity", "<f4")])
 assert VOICE_DESC.itemsize == 80 and VOICE_STATE.itemsize == 32
+assert PATCH.itemsize == 144 and NOTE_EVENT.itemsize == 16
 
 # every symbol include/s2_cuda.h declares: (restype, argtypes)
 _vp, _sz, _u32, _u8, _f, _i = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint8, C.c_float, C.c_int
@@ -69,6 +73,10 @@ SYMBOLS = {
     "s2_synth_note_off": (_i, [_vp, _u8]),
     "s2_synth_sample": (_i, [_vp, _vp, _sz, _u32]),
     "s2_synth_voice_info": (_i, [_vp, _i, C.POINTER(_u8), C.POINTER(_u32), C.POINTER(_u32), _vp]),
+    "s2_default_patch": (None, [_vp]),
+    "s2_patch_parse": (_i, [C.c_char_p, _u32, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "s2_synth_set_patch": (_i, [_vp, _vp]),
+    "s2_synth_render_score": (_i, [_vp, _vp, _sz, _u32, _vp, _sz]),
 }
 
 

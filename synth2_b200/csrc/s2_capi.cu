@@ -43,6 +43,21 @@ int fail(int code, const char* fmt, ...) {
 
 bool finite_nonneg(float x) { return std::isfinite(x) && x >= 0.0f; }
 
+}  // namespace
+
+namespace s2 {
+// error reporting for the other host translation units of the library (s2_patch.cpp)
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace s2
+
+namespace {
+
 int validate_voice(const s2_voice_desc& d, size_t index) {
     if (d.osc_kind > S2_OSC_SINE) return fail(S2_ERR_INVALID, "voice %zu: osc_kind %u", index, d.osc_kind);
     if (!(std::isfinite(d.pitch_hz) && d.pitch_hz > 0.0f))
@@ -829,6 +844,9 @@ struct s2_synth {
     // note events that arrived before the bank exists
     s2_voice_desc pending[kNumVoices];
     bool dirty[kNumVoices] = {};
+    s2_patch patch;             // what note_on plays: Synth::default_config() unless s2_synth_set_patch changed it
+    float* d_score = nullptr;   // device buffer of s2_synth_render_score
+    size_t score_cap = 0;
 };
 
 namespace {
@@ -864,6 +882,7 @@ int s2_synth_new(int device, s2_synth** out) {
     if (!s) return fail(S2_ERR_NOMEM, "out of host memory");
     s->device = device;
     for (int i = 0; i < kNumVoices; i++) s2_default_voice(&s->pending[i]);   // Voice::default(): free slot
+    s2_default_patch(&s->patch);
     *out = s;
     return S2_OK;
 }
@@ -871,6 +890,7 @@ int s2_synth_new(int device, s2_synth** out) {
 void s2_synth_free(s2_synth* s) {
     if (!s) return;
     s2_bank_destroy(s->bank);
+    if (s->d_score) cudaFree(s->d_score);
     delete s;
 }
 
@@ -886,8 +906,7 @@ int s2_synth_note_on(s2_synth* s, uint8_t note, float velocity) {
     v.has_current = true;
     v.has_release = false;
     v.release = 0;
-    s2_voice_desc d;
-    s2_default_voice(&d);
+    s2_voice_desc d = s->patch.voice;
     d.pitch_hz = s2_note_to_pitch(note);
     d.frame_offset = 0;
     d.release_offset = S2_NO_RELEASE;
@@ -917,12 +936,11 @@ int s2_synth_note_off(s2_synth* s, uint8_t note) {
     return s2_bank_release_voice(s->bank, (size_t)found);
 }
 
-int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample_rate) {
-    if (!s || (!h_buffer && frames)) return fail(S2_ERR_INVALID, "null argument");
-    if (frames == 0) return S2_OK;
+// The bank is created by the first render, which is when the rate is known (synth.rs:156 takes it per call).
+static int synth_ensure_bank(s2_synth* s, uint32_t sample_rate) {
     if (s->bank && s->sample_rate != sample_rate) {
-        // The reference takes the rate per call (synth.rs:156).  Changing it mid-stream re-derives
-        // every rate-dependent constant; carry the DSP state over into a bank built for the new rate.
+        // Changing the rate mid-stream re-derives every rate-dependent constant; carry the DSP state over
+        // into a bank built for the new rate.
         std::vector<s2_voice_state> st(kNumVoices);
         std::vector<s2_voice_desc> ds(kNumVoices);
         int rc = s2_bank_get_state(s->bank, st.data());
@@ -932,7 +950,7 @@ int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample
             if (!s->dirty[i]) ds[i].frame_offset = st[i].frame_offset;
         }
         s2_bank* nb = nullptr;
-        rc = s2_bank_create(s->device, sample_rate, S2_FILTER_ONE_POLE, kNumVoices, ds.data(), nullptr, &nb);
+        rc = s2_bank_create(s->device, sample_rate, s->patch.filter_kind, kNumVoices, ds.data(), nullptr, &nb);
         if (rc) return rc;
         for (int i = 0; i < kNumVoices; i++)
             if (s->dirty[i]) { memset(&st[i], 0, sizeof st[i]); st[i].frame_offset = ds[i].frame_offset; }
@@ -944,14 +962,83 @@ int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample
         for (int i = 0; i < kNumVoices; i++) s->dirty[i] = false;
     }
     if (!s->bank) {
-        int rc = s2_bank_create(s->device, sample_rate, S2_FILTER_ONE_POLE, kNumVoices, s->pending, nullptr, &s->bank);
+        int rc = s2_bank_create(s->device, sample_rate, s->patch.filter_kind, kNumVoices, s->pending, nullptr, &s->bank);
         if (rc) return rc;
         s->sample_rate = sample_rate;
         for (int i = 0; i < kNumVoices; i++) s->dirty[i] = false;
     }
-    int rc = synth_flush(s);
+    return synth_flush(s);
+}
+
+int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample_rate) {
+    if (!s || (!h_buffer && frames)) return fail(S2_ERR_INVALID, "null argument");
+    if (frames == 0) return S2_OK;
+    if (sample_rate == 0) return fail(S2_ERR_INVALID, "sample_rate must be > 0");
+    int rc = synth_ensure_bank(s, sample_rate);
     if (rc) return rc;
     return s2_bank_render_bus_host(s->bank, frames, nullptr, 0, h_buffer);
+}
+
+int s2_synth_set_patch(s2_synth* s, const s2_patch* patch) {
+    if (!s || !patch) return fail(S2_ERR_INVALID, "null argument");
+    if (patch->filter_kind > S2_FILTER_BIQUAD_LP) return fail(S2_ERR_INVALID, "filter_kind %u", patch->filter_kind);
+    s2_voice_desc probe = patch->voice;
+    probe.pitch_hz = 440.0f;                    // the template's pitch is replaced per note
+    int rc = validate_voice(probe, 0);
+    if (rc) return rc;
+    if (patch->filter_kind != s->patch.filter_kind) {
+        for (int i = 0; i < kNumVoices; i++)
+            if (s->voices[i].has_current)
+                return fail(S2_ERR_INVALID, "the filter kind can only change while no voice is sounding");
+        s2_bank_destroy(s->bank);               // the next render builds a bank of the new kind
+        s->bank = nullptr;
+        for (int i = 0; i < kNumVoices; i++) { s2_default_voice(&s->pending[i]); s->dirty[i] = false; }
+    }
+    s->patch = *patch;
+    s->patch.name[sizeof s->patch.name - 1] = 0;
+    return S2_OK;
+}
+
+// main.rs:138-147: messages are applied between 16-frame chunks, i.e. before the first chunk that starts at
+// or after their arrival
+static uint64_t score_quantise(uint64_t frame) { return (frame + 15u) & ~(uint64_t)15u; }
+
+int s2_synth_render_score(s2_synth* s, const s2_note_event* events, size_t n_events, uint32_t sample_rate,
+                          float* h_buffer, size_t frames) {
+    if (!s || (!h_buffer && frames) || (!events && n_events)) return fail(S2_ERR_INVALID, "null argument");
+    if (sample_rate == 0) return fail(S2_ERR_INVALID, "sample_rate must be > 0");
+    for (size_t i = 0; i < n_events; i++) {
+        if (i && events[i].frame < events[i - 1].frame) return fail(S2_ERR_INVALID, "event %zu is out of time order", i);
+        if (events[i].on > 1) return fail(S2_ERR_INVALID, "event %zu: on must be 0 or 1", i);
+        if (events[i].frame > 0xFFFFFFFFFFFFFFF0ull) return fail(S2_ERR_INVALID, "event %zu: time out of range", i);
+    }
+    if (frames == 0) return S2_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (frames > s->score_cap) {
+        if (s->d_score) CUDA_TRY(cudaFree(s->d_score));
+        s->d_score = nullptr; s->score_cap = 0;
+        CUDA_TRY(cudaMalloc(&s->d_score, frames * sizeof(float)));
+        s->score_cap = frames;
+    }
+    size_t pos = 0, i = 0;
+    while (pos < frames) {
+        while (i < n_events && score_quantise(events[i].frame) <= pos) {
+            const int rc = events[i].on ? s2_synth_note_on(s, events[i].note, events[i].velocity)
+                                        : s2_synth_note_off(s, events[i].note);
+            if (rc < 0) return rc;
+            i++;
+        }
+        size_t next = frames;
+        if (i < n_events && score_quantise(events[i].frame) < frames) next = (size_t)score_quantise(events[i].frame);
+        int rc = synth_ensure_bank(s, sample_rate);          // uploads the voices the events touched
+        if (rc) return rc;
+        rc = bank_render_impl(s->bank, next - pos, nullptr, 0, s->d_score + pos, s2::TRACE_NONE);
+        if (rc) return rc;
+        pos = next;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_buffer, s->d_score, frames * sizeof(float), cudaMemcpyDeviceToHost, s->bank->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->bank->stream));
+    return S2_OK;
 }
 
 int s2_synth_voice_info(s2_synth* s, int slot, uint8_t* note, uint32_t* current_offset_out,

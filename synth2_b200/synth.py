@@ -63,6 +63,24 @@ class Synth:
         assert isinstance(buffer, np.ndarray) and buffer.dtype == np.float32 and buffer.flags.c_contiguous
         check(lib().s2_synth_sample(self._h, ptr(buffer), buffer.size, int(sample_rate)))
 
+    # -- beyond the reference's API: a patch other than default_config(), and the
+    #    s2_bin loop (apply the MIDI messages that arrived, then sample 16 frames: main.rs:138-147) as one call
+    def set_patch(self, patch):
+        """Notes started from now on play `patch` (a synth2_b200.patch.Patch)."""
+        check(lib().s2_synth_set_patch(self._h, ptr(patch.record)))
+
+    def render_score(self, events: np.ndarray, frames: int, sample_rate: int, out: np.ndarray = None) -> np.ndarray:
+        """Renders `frames` mono frames, applying each NOTE_EVENT before the first 16-frame chunk that starts
+        at or after its arrival frame."""
+        from ._lib import NOTE_EVENT
+        events = np.ascontiguousarray(events, dtype=NOTE_EVENT)
+        if out is None:
+            out = np.empty(int(frames), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size >= frames
+        check(lib().s2_synth_render_score(self._h, ptr(events) if events.size else None, events.size,
+                                          int(sample_rate), ptr(out), int(frames)))
+        return out[:frames]
+
     def voice_info(self, slot: int):
         """Test hook: (in_use, note, current_frame_offset|None, release_frame_offset|None, state)."""
         note, cur, rel = C.c_uint8(), C.c_uint32(), C.c_uint32()

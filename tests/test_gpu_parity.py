@@ -694,3 +694,96 @@ def test_time_split_argument_errors():
         bank.set_pipeline(2)
         with pytest.raises(s2.S2Error):
             bank.set_time_split(True)
+
+
+# ------------------------------------------------------------------------------ patch files and scores
+
+from synth2_b200 import patch as s2patch
+
+
+def test_render_score_is_the_s2_bin_loop():
+    """s2_synth_render_score == apply the events that arrived, then Synth::sample 16 frames (main.rs:138-147).
+    Config-1 fixture plus events that arrive off the 16-frame grid; against the oracle's Synth driven chunk by
+    chunk, and bit-for-bit against this library's own note_on / note_off / sample calls."""
+    total = 60000
+    raw = [(0, "on", 69), (1000, "on", 57), (12345, "on", 76), (24001, "off", 69), (40000, "off", 57), (40007, "off", 76),
+           (59999, "on", 50)]                                   # the last one quantises to 60,000: never applied
+    quantised = [((f + 15) & ~15, op, n) for f, op, n in raw]
+    ref = run_script(oracle.OracleSynth(), total, quantised, chunk=16)
+    syn = s2.Synth()
+    got = syn.render_score(s2patch.make_events(raw), total, SR)
+    assert_parity(ref, got, "render_score vs oracle Synth")
+    stepwise = run_script(s2.Synth(), total, quantised)
+    assert got.tobytes() == stepwise.tobytes()
+    assert not syn.voice_info(3)[0]                             # note 50 was not started
+    # the synth carries on: a second call continues the voices
+    more = syn.render_score(s2patch.make_events([]), 4800, SR)
+    assert more.shape == (4800,) and np.all(np.isfinite(more))
+    syn.close()
+
+
+@pytest.mark.parametrize("kind", ["one_pole", "biquad"])
+def test_custom_patch_renders_like_the_oracle(kind):
+    """A patch other than default_config(): every static_config::Layer field set, two overlapping notes.
+    Expected = the oracle's process_layer_buf_simd per voice, mixed in slot order (synth.rs:176-202)."""
+    text = f"""synth lead {{
+        osc {{ kind square; gain 0.75 }}  noise 0.125
+        lpf {{ freq 900; kind {kind}; damping 0.6 }}
+        amp_env {{ attack 5; decay 40; sustain 0.625; release 120 }}
+        mod_env {{ attack 2; decay 60; sustain 0.25; release 30 }}
+        modulations {{ mod_env_to_lpf_freq 1.5 }}
+    }}
+    score {{ on 0 57; on 4800 64; off 14400 57; off 19200 64 }}"""
+    p = s2patch.parse(text, SR)
+    fk = p.filter_kind
+    total = 28800
+    syn = s2.Synth()
+    syn.set_patch(p)
+    got = syn.render_score(p.events, total, SR)
+    syn.close()
+    # oracle: one voice per note, each rendered from its own note-on
+    mix = np.zeros(total, dtype=np.float32)
+    for on, off, note in ((0, 14400, 57), (4800, 19200, 64)):
+        v = np.zeros(1, dtype=s2.VOICE_DESC)
+        v[0] = p.voice
+        v["pitch_hz"] = s2.note_to_pitch(note)
+        v["active"] = 1
+        v["frame_offset"] = 0
+        v["release_offset"] = off - on
+        st = oracle.bank_init_states(v)
+        o, _ = oracle.bank_render(v, st, SR, fk, total - on, want_bus=False)
+        mix[on:] = mix[on:] + o[0]
+    assert_parity(mix, got, f"custom patch ({kind})")
+    assert np.max(np.abs(mix)) > 0.1
+
+
+def test_set_patch_rules():
+    syn = s2.Synth()
+    bq = s2patch.parse("synth b { lpf { kind biquad; freq 500 } }")
+    syn.note_on(60)
+    with pytest.raises(s2.S2Error):
+        syn.set_patch(bq)                                      # filter kind cannot change under a sounding voice
+    syn.close()
+    bad = s2patch.default_patch()
+    bad.record["voice"]["amp_attack_ms"] = -1.0
+    syn = s2.Synth()
+    with pytest.raises(s2.S2Error):
+        syn.set_patch(bad)
+    with pytest.raises(s2.S2Error):
+        syn.render_score(s2patch.make_events([(10, "on", 60), (5, "off", 60)]), 100, SR)
+    syn.close()
+
+
+def test_render_cli(tmp_path):
+    from synth2_b200 import render
+    src = tmp_path / "example.synth2"
+    src.write_text("synth mySynth {\n\n}\n")
+    out = tmp_path / "out.f32"
+    assert render.main([str(src), "--seconds", "0.5", "--rate", "48000", "-o", str(out), "--note", "69"]) == 0
+    got = np.fromfile(out, dtype="<f4")
+    assert got.shape == (24000,)
+    ref = run_script(oracle.OracleSynth(), 24000, [(0, "on", 69), (18000, "off", 69)])
+    assert_parity(ref, got, "render CLI")
+    wav = tmp_path / "out.wav"
+    assert render.main([str(src), "--seconds", "0.1", "-o", str(wav)]) == 0
+    assert wav.read_bytes()[:4] == b"RIFF"

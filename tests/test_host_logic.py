@@ -266,3 +266,86 @@ def test_math_kernels_round_once_on_cpu(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout
     assert "special values ok" in out.stdout
+
+
+# ---- .synth2 patch files (csrc/s2_patch.cpp; runs without a GPU) -------------------------------
+
+from synth2_b200 import patch as s2patch
+
+EXAMPLE_SYNTH2 = "synth mySynth {\n\n}\n"          # the reference's example.synth2, verbatim
+
+
+def test_patch_example_is_the_default_patch():
+    p = s2patch.parse(EXAMPLE_SYNTH2)
+    assert p.name == "mySynth" and p.filter_kind == s2.FILTER_ONE_POLE and p.events.size == 0
+    assert p.voice.tobytes() == s2.default_voice(1)[0].tobytes()
+    assert s2patch.default_patch().voice.tobytes() == p.voice.tobytes()
+
+
+def test_patch_fields_follow_static_config_layer():
+    p = s2patch.parse("""
+        // every field of static_config::Layer
+        synth lead {
+            osc { kind triangle; gain 0.75 }
+            noise 0.125                       # Unipolar<1>
+            lpf { freq 1200; kind biquad; damping 0.5 }
+            amp_env { attack 5; decay 50; sustain 0.625; release 300 }
+            mod_env { attack 1 decay 100 sustain 0.25 release 10 }
+            modulations { mod_env_to_osc_freq -0.5; mod_env_to_lpf_freq 1.5 }
+        }
+        score {
+            on 0 69
+            on 0.5s 72 0.5
+            off 1s 69;  off 1500ms 72
+        }
+    """, sample_rate=48000)
+    v = p.voice
+    assert p.name == "lead" and p.filter_kind == s2.FILTER_BIQUAD_LP
+    assert v["osc_kind"] == s2.OSC_TRIANGLE and v["osc_gain"] == 0.75 and v["noise_amt"] == 0.125
+    assert v["lpf_freq_hz"] == 1200.0 and v["damping"] == 0.5
+    assert [v[k] for k in ("amp_attack_ms", "amp_decay_ms", "amp_sustain", "amp_release_ms")] == [5.0, 50.0, 0.625, 300.0]
+    assert [v[k] for k in ("mod_attack_ms", "mod_decay_ms", "mod_sustain", "mod_release_ms")] == [1.0, 100.0, 0.25, 10.0]
+    assert v["mod_env_to_osc_freq"] == -0.5 and v["mod_env_to_lpf_freq"] == 1.5
+    assert list(p.events["frame"]) == [0, 24000, 48000, 72000]
+    assert list(p.events["note"]) == [69, 72, 69, 72] and list(p.events["on"]) == [1, 1, 0, 0]
+    assert list(p.events["velocity"][:2]) == [1.0, 0.5]
+    # the same score at another rate
+    assert list(s2patch.parse("synth a { } score { on 10ms 60; off 1s 60 }", 44100).events["frame"]) == [441, 44100]
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("synth x { osc { kind pulse } }", "unknown oscillator 'pulse'"),
+    ("synth x { noise 2 }", "outside [0, 1]"),                          # units.rs:55-65 range checks
+    ("synth x { modulations { mod_env_to_lpf_freq 11 } }", "outside [-10, 10]"),
+    ("synth x {\n  lpf { freq 100 }\n  reverb 1\n}", "line 3: unknown field reverb"),
+    ("synth x {", "expected '}'"),
+    ("score { on 0 69 }", "no synth block"),
+    ("synth x { } synth y { }", "more than one synth block"),
+    ("synth x { } score { on 10 69; off 5 69 }", "time order"),
+    ("synth x { } score { on 0 128 }", "MIDI note"),
+    ("synth x { } score { on 1.5 60 }", "whole number of frames"),
+    ("synth x { lpf { freq 10kHz } }", "unknown unit"),
+    ("synth x { amp_env { sustain 1.5 } }", "amp_env.sustain"),
+])
+def test_patch_errors_name_the_line_and_field(text, needle):
+    with pytest.raises(s2.S2Error) as e:
+        s2patch.parse(text)
+    assert needle in str(e.value) and "patch line" in str(e.value)
+
+
+def test_patch_struct_layouts():
+    assert s2.PATCH.itemsize == 144 and s2.PATCH.fields["filter_kind"][1] == 80 and s2.PATCH.fields["name"][1] == 84
+    assert s2.NOTE_EVENT.itemsize == 16 and s2.NOTE_EVENT.fields["velocity"][1] == 12
+    assert re.search(r"char name\[60\];", HEADER) and re.search(r"\} s2_note_event;\s+/\* 16 bytes \*/", HEADER)
+
+
+def test_wav_writer_roundtrip(tmp_path):
+    from synth2_b200.render import write_wav_f32
+    x = np.linspace(-1, 1, 1000, dtype=np.float32)
+    path = tmp_path / "x.wav"
+    write_wav_f32(path, x, 48000)
+    raw = path.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE" and int.from_bytes(raw[4:8], "little") == len(raw) - 8
+    i = raw.index(b"data")
+    assert int.from_bytes(raw[i + 4:i + 8], "little") == 4000
+    assert np.frombuffer(raw[i + 8:], dtype="<f4").tobytes() == x.tobytes()
