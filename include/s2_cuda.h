@@ -223,6 +223,29 @@ int s2_synth_set_patch(s2_synth* synth, const s2_patch* patch);
 int s2_synth_render_score(s2_synth* synth, const s2_note_event* events, size_t n_events, uint32_t sample_rate,
                           float* h_buffer, size_t frames);
 
+/* ---- Player hand-off: s2_bin/src/audio_player.rs without the cpal device ----
+ *
+ * Two mono buffers of S2_PLAYER_BUFFER_FRAMES frames (audio_player.rs:21-24) circulate between an internal
+ * synth thread (main.rs:120-160: take an empty buffer, apply the note messages that arrived, render, hand
+ * it over) and the caller's audio callback.  s2_player_fill is `fill_buffer` (audio_player.rs:136-199) for
+ * f32 output: drain the buffer in hand, take at most one new filled buffer without blocking, write every
+ * sample to all `channels` interleaved channels, zero-fill the rest (an underrun is counted, never waited
+ * for).  It returns the number of frames that came from rendered buffers.  note_on / note_off may be called
+ * from any thread; fill from one thread at a time.
+ */
+#define S2_PLAYER_BUFFER_FRAMES 2048
+typedef struct s2_player s2_player;
+int s2_player_new(int device, uint32_t sample_rate, s2_player** out);     /* idle until s2_player_start */
+void s2_player_free(s2_player* player);
+int s2_player_set_patch(s2_player* player, const s2_patch* patch);        /* before s2_player_start */
+int s2_player_start(s2_player* player);
+int s2_player_note_on(s2_player* player, uint8_t note, float velocity);
+int s2_player_note_off(s2_player* player, uint8_t note);
+int64_t s2_player_fill(s2_player* player, float* out, size_t frames, uint32_t channels);
+int s2_player_stats(s2_player* player, uint64_t* buffers_rendered, uint64_t* underruns, uint64_t* frames_played);
+/* blocks until `n_rendered` buffers have been handed over (0) or `timeout_ms` passed (1) */
+int s2_player_wait_buffers(s2_player* player, uint64_t n_rendered, uint32_t timeout_ms);
+
 /* test hook: slot contents; returns 1 if the slot has a current_frame_offset, 0 if free */
 int s2_synth_voice_info(s2_synth* synth, int slot, uint8_t* note, uint32_t* current_offset,
                         uint32_t* release_offset, s2_voice_state* state);

@@ -6,6 +6,7 @@ the host-side mirror of the reference interface:
     Synth        synth::Synth          s2_lib/src/try3/synth.rs:9-203
     VoiceBank    the batched form of   process::process_layer_buf_simd (process.rs:14-49)
     bankgen      synthetic voice banks of BASELINE.json's shapes
+    Player       the two-buffer hand-off to an audio callback   s2_bin/src/audio_player.rs
     patch        `.synth2` patch + score files (example.synth2); `python -m synth2_b200.render` renders one
 
 Importing the package does not need a GPU; creating a Synth / VoiceBank does, and fails loudly
@@ -15,10 +16,11 @@ from ._lib import (FILTER_BIQUAD_LP, FILTER_ONE_POLE, NO_RELEASE, NOTE_EVENT, OS
                    OSC_TRIANGLE, PATCH, VOICE_DESC, VOICE_STATE, S2Error, lib)
 from . import patch
 from .bank import VoiceBank, default_voice, note_to_pitch
+from .player import Player
 from .synth import FrameOffset, Note, Synth, Velocity
 
 __all__ = [
-    "Synth", "Note", "Velocity", "FrameOffset", "VoiceBank", "default_voice", "note_to_pitch",
+    "Synth", "Player", "Note", "Velocity", "FrameOffset", "VoiceBank", "default_voice", "note_to_pitch",
     "VOICE_DESC", "VOICE_STATE", "PATCH", "NOTE_EVENT", "patch", "S2Error", "lib", "NO_RELEASE",
     "OSC_SQUARE", "OSC_SAW", "OSC_TRIANGLE", "OSC_SINE", "FILTER_ONE_POLE", "FILTER_BIQUAD_LP",
 ]

@@ -77,6 +77,15 @@ SYMBOLS = {
     "s2_patch_parse": (_i, [C.c_char_p, _u32, _vp, _vp, _sz, C.POINTER(_sz)]),
     "s2_synth_set_patch": (_i, [_vp, _vp]),
     "s2_synth_render_score": (_i, [_vp, _vp, _sz, _u32, _vp, _sz]),
+    "s2_player_new": (_i, [_i, _u32, C.POINTER(_vp)]),
+    "s2_player_free": (None, [_vp]),
+    "s2_player_set_patch": (_i, [_vp, _vp]),
+    "s2_player_start": (_i, [_vp]),
+    "s2_player_note_on": (_i, [_vp, _u8, _f]),
+    "s2_player_note_off": (_i, [_vp, _u8]),
+    "s2_player_fill": (C.c_int64, [_vp, _vp, _sz, _u32]),
+    "s2_player_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "s2_player_wait_buffers": (_i, [_vp, C.c_uint64, _u32]),
 }
 
 

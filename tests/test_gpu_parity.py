@@ -787,3 +787,61 @@ def test_render_cli(tmp_path):
     wav = tmp_path / "out.wav"
     assert render.main([str(src), "--seconds", "0.1", "-o", str(wav)]) == 0
     assert wav.read_bytes()[:4] == b"RIFF"
+
+
+# ------------------------------------------------------------------------------ player hand-off
+
+def test_player_fill_is_the_reference_callback():
+    """audio_player.rs `fill_buffer`: mono -> all channels, at most one new buffer per callback, zeros on
+    underrun; the synth thread applies the notes that arrived before it renders a buffer (main.rs:138-147)."""
+    B = s2.player.BUFFER_FRAMES
+    with s2.Player(SR, start=False) as pl:
+        out = np.full((512, 2), 7.0, np.float32)
+        assert pl.fill(out) == 0 and np.all(out == 0.0)               # nothing rendered yet: zeros, counted
+        assert pl.stats()["underruns"] == 1
+        pl.note_on(69)
+        pl.start()
+        assert pl.wait_buffers(2)                                      # both buffers in circulation are filled
+        ref = run_script(oracle.OracleSynth(), 3 * B, [(0, "on", 69)])
+        got = []
+        # callbacks of 600 stereo frames: buffer boundaries fall inside a callback
+        for _ in range(8):
+            out = np.full((600, 2), 7.0, np.float32)
+            n = pl.fill(out)
+            assert np.array_equal(out[:, 0], out[:, 1])
+            assert np.all(out[n:] == 0.0)
+            got.append(out[:n, 0].copy())
+            pl.wait_buffers(pl.stats()["buffers_rendered"] + 1, 200)   # let the synth thread refill
+        got = np.concatenate(got)
+        assert got.size >= 2 * B
+        assert_parity(ref[:got.size], got, "player stream")
+        # a callback larger than a buffer takes one buffer and pads (audio_player.rs:150-152)
+        pl.wait_buffers(pl.stats()["buffers_rendered"] + 2, 500)
+        big = np.full(3 * B, 7.0, np.float32)
+        n = pl.fill(big)
+        assert n <= 2 * B and np.all(big[n:] == 0.0)
+        st = pl.stats()
+        assert st["frames_played"] == got.size + n and st["buffers_rendered"] >= 4
+
+
+def test_player_note_off_and_patch():
+    p = s2patch.parse("synth s { osc { kind sine } lpf { freq 4000 } amp_env { attack 1; decay 1; sustain 1; release 5 } "
+                      "mod_env { decay 0 } modulations { mod_env_to_lpf_freq 0 } }")
+    with s2.Player(SR, patch=p, start=False) as pl:
+        pl.note_on(60)
+        pl.start()
+        assert pl.wait_buffers(2)
+        pl.note_off(60)                                                # applied before the third buffer
+        mono = np.zeros(s2.player.BUFFER_FRAMES, np.float32)
+        chunks = []
+        for _ in range(4):
+            n = pl.fill(mono)
+            chunks.append(mono[:n].copy())
+            pl.wait_buffers(pl.stats()["buffers_rendered"] + 1, 300)
+        x = np.concatenate(chunks)
+        assert x.size == 4 * s2.player.BUFFER_FRAMES
+        assert np.max(np.abs(x[:4096])) > 0.5                          # sounding
+        assert np.all(x[3 * 2048 + 1024:] == 0.0)                      # released 5 ms into the third buffer
+        with pytest.raises(s2.S2Error):
+            lib_rc = s2.lib().s2_player_set_patch(pl._h, s2._lib.ptr(p.record))
+            s2._lib.check(lib_rc)                                      # after start
