@@ -721,7 +721,7 @@ struct Cold {
     uint32_t flags;        // bit 0 active, bit 1 mod envelope matters
 };
 constexpr int kColdWords = (sizeof(Cold) / 4) | 1;
-constexpr int kRowPtrWords = 18;   // 8 row pointers (16 words) + 2 pad: conflict-free LDS.64
+constexpr int kRowPtrWords = 2;    // one 64-bit output-row base per tile row (0 = the row has no output)
 
 template <int NV>
 __host__ __device__ constexpr size_t warp_smem_floats() {

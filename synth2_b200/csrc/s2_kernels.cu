@@ -158,15 +158,17 @@ render_kernel(const RenderArgs a) {
     // kind-uniform warps (P_ROW).  Transposed write-back: lanes 8q..8q+7 cover 128 contiguous bytes of
     // tile row 4*i + q, so each STG.128 of the warp writes four full 128-byte lines.
     const int q = lane >> 3, c4 = (lane & 7) * 4;
+    // rp[tile row] = base address of that voice's output row (0 = none): 32*NV 64-bit words per warp.  The four
+    // q-groups of a store read four neighbouring words (broadcast inside a group): conflict-free LDS.64.
+    unsigned long long* rp = reinterpret_cast<unsigned long long*>(cold_base + kRows * kColdWords);
     bool lane_rows_ok = gout != nullptr;
 #pragma unroll
-    for (int i = 0; i < 8 * NV; i++) {
-        const int row = 4 * i + q;                 // tile row = e * 32 + source lane
-        const uint32_t r = __shfl_sync(0xffffffffu, cold((4 * i) / 32).out_row, row & 31);
+    for (int e = 0; e < NV; e++) {
+        const uint32_t r = cold(e).out_row;
         lane_rows_ok &= r != 0xffffffffu;
-        reinterpret_cast<unsigned long long*>(cold_base + kRows * kColdWords)[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)] =
-            (gout && r != 0xffffffffu) ? reinterpret_cast<unsigned long long>(gout + (size_t)r * stride + c4) : 0ull;
+        rp[e * 32 + lane] = (gout && r != 0xffffffffu) ? reinterpret_cast<unsigned long long>(gout + (size_t)r * stride) : 0ull;
     }
+    __syncwarp();
     const bool all_rows = __all_sync(0xffffffffu, lane_rows_ok);   // every tile row has an output row
     float* __restrict__ gbus = a.bus_partials ? a.bus_partials + (size_t)gwarp * frames : nullptr;
 
@@ -358,12 +360,11 @@ render_kernel(const RenderArgs a) {
             // four q-groups are added by two butterfly shuffles (a fixed tree: deterministic; banks of <= 32
             // voices use the reference's sequential order below).  Three straight-line variants so that the
             // common one carries no predicates.
-            const size_t tb = (size_t)t0 * sizeof(float);
-            const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(cold_base + kRows * kColdWords);
+            const size_t tb = ((size_t)t0 + (size_t)c4) * sizeof(float);
             if (all_rows && !wide_bus) {
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
-                    char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
+                    char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
                     const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
                     __stcs(reinterpret_cast<float4*>(dst + tb), val);
                 }
@@ -371,7 +372,7 @@ render_kernel(const RenderArgs a) {
                 float4 val[8 * NV];
 #pragma unroll
                 for (int i = 0; i < 8 * NV; i++) {
-                    char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
+                    char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
                     val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
                     __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
                 }
@@ -382,7 +383,7 @@ render_kernel(const RenderArgs a) {
                 for (int i = 0; i < 8 * NV; i++) {
                     val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
                     if (gout) {
-                        char* dst = reinterpret_cast<char*>(rp[((i / 8) * 32 + lane) * (kRowPtrWords / 2) + (i & 7)]);
+                        char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
                         if (dst) __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
                     }
                 }
