@@ -845,3 +845,38 @@ def test_player_note_off_and_patch():
         with pytest.raises(s2.S2Error):
             lib_rc = s2.lib().s2_player_set_patch(pl._h, s2._lib.ptr(p.record))
             s2._lib.check(lib_rc)                                      # after start
+
+
+# ------------------------------------------------------------------------------ out-of-bounds guards
+
+@pytest.mark.parametrize("mode", ["default", "pipelined", "time_split"])
+@pytest.mark.parametrize("V,frames", [(70, 1024), (1000, 2048), (33, 1000)])
+def test_no_write_outside_the_output_rows(mode, V, frames):
+    """Guard rows before / after the output block and guard columns after each row's `frames` must keep their
+    sentinel: the transposed write-back, the ragged tail, the inactive-row clearing and the time-split
+    segments all stay inside [row, row + frames)."""
+    if mode == "time_split" and frames % 1024:
+        pytest.skip("time-split needs whole 1,024-frame multiples (falls back otherwise: covered by 'default')")
+    v = bank_for(0, V, 8 * frames, mod_to_lpf_choices=(0.0,))
+    v["active"][3::7] = 0
+    stride = ((frames + 3) & ~3) + 8
+    buf = torch.full((V + 2, stride), -777.0, device="cuda", dtype=torch.float32)
+    bus = torch.full((frames + 64,), -777.0, device="cuda", dtype=torch.float32)
+    with s2.VoiceBank(v, SR, 0) as bank:
+        if mode == "pipelined":
+            bank.set_pipeline(3)
+        if mode == "time_split":
+            bank.set_time_split(True)
+        for _ in range(2):
+            bank.render(frames, buf[1:], stride, None if mode == "time_split" else bus[32:])
+        bank.sync()
+        if mode == "time_split":
+            assert bank.time_split_blocks == 2
+    out = buf.cpu().numpy()
+    assert np.all(out[0] == -777.0) and np.all(out[-1] == -777.0)
+    assert np.all(out[1:-1, frames:] == -777.0)
+    assert np.all(np.isfinite(out[1:-1, :frames])) and not np.any(out[1:-1, :frames] == -777.0)
+    b = bus.cpu().numpy()
+    assert np.all(b[:32] == -777.0) and np.all(b[32 + frames:] == -777.0)
+    if mode != "time_split":
+        assert not np.any(b[32:32 + frames] == -777.0)
