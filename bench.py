@@ -162,6 +162,29 @@ def cpu_baseline(args, bankgen):
                       f"{cores} threads; C port of the reference's x16 path (Rust toolchain absent)"}
 
 
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to stdout at
+# NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr for the whole run and the result line goes to a
+# saved copy of the original stdout.
+_RESULT_FD = None
+
+
+def capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the C port: the Rust crate
     cannot be built in this image) on all host cores; each step is a bounded sample."""
@@ -185,7 +208,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = nv * sum(frames) / dt
     sample = f"{nv} voices x {sum(frames)} frames of the config-3 bank per run, {cores} threads, C port of the reference x16 path"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "voice-samples/sec (osc+biquad, 48 kHz)", "value": value,
         "unit": "voice-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -195,13 +218,14 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------
 
 def main():
     args = parse()
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -218,9 +242,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout at
-        # NCCL_DEBUG=VERSION) goes to stderr with the rest of its log
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the renderer has no CPU path")
@@ -344,7 +365,7 @@ def main():
         cpu = cpu_baseline(args, bankgen)
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "voice-samples/sec (osc+biquad, 48 kHz)", "value": value, "unit": "voice-samples/s",
             "n_gpus": world, "steps": len(frames), "warmup": max(args.warmup, 3), "ms_per_step": ms / len(frames),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -355,7 +376,7 @@ def main():
                        "master_bus": bool(want_master), "pipeline_voice_ranges": int(args.pipeline)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-        }), flush=True)
+        })
     bank.close()
     if world > 1:
         dist.destroy_process_group()
