@@ -195,12 +195,12 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         th = __fdiv_rn(th, sr);
         float s, co;
         s2_sincosf(th, &s, &co);
-        const float hd = __fdiv_rn(damp, 2.0f);
+        const float hd = __fmul_rn(damp, 0.5f);                      // damp / 2.0: scaling by a power of two, same bits
         const float num = __fsub_rn(1.0f, __fmul_rn(hd, s));
         const float den = __fadd_rn(1.0f, __fmul_rn(hd, s));
         const float beta = __fmul_rn(0.5f, __fdiv_rn(num, den));
         const float gamma = __fmul_rn(__fadd_rn(0.5f, beta), co);
-        const float alpha = __fdiv_rn(__fsub_rn(__fadd_rn(0.5f, beta), gamma), 4.0f);
+        const float alpha = __fmul_rn(__fsub_rn(__fadd_rn(0.5f, beta), gamma), 0.25f);      // ... / 4.0, likewise
         // y = 2*(alpha*s + gamma*y1 - beta*y2): scaling by 2 commutes with round-to-nearest, so the
         // doubling is folded into the coefficients (exact unless an intermediate is subnormal).
         c.c0 = __fmul_rn(2.0f, alpha);
