@@ -193,18 +193,18 @@ def run_reference(args):
         return
     from synth2_b200 import bankgen
     cores = os.cpu_count() or 1
-    nv = max(cores * 8, 64)
+    nv = max(cores * 64, 1024)          # enough voices per thread that thread start-up does not show (same as cpu_baseline)
     voices = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle
     st = oracle.bank_init_states(voices)
     frames = step_frames(args.steps, args.block)
     for _ in range(args.warmup):
-        oracle.bank_render(voices, st, SR, FILTER_BIQUAD, args.block, want_bus=False, nthreads=cores)
+        oracle.bank_render(voices, st, SR, FILTER_BIQUAD, args.block, want_voices=False, want_bus=False, nthreads=cores)
     st = oracle.bank_init_states(voices)
     t0 = time.perf_counter()
     for fr in frames:
-        oracle.bank_render(voices, st, SR, FILTER_BIQUAD, fr, want_bus=False, nthreads=cores)
+        oracle.bank_render(voices, st, SR, FILTER_BIQUAD, fr, want_voices=False, want_bus=False, nthreads=cores)
     dt = time.perf_counter() - t0
     value = nv * sum(frames) / dt
     sample = f"{nv} voices x {sum(frames)} frames of the config-3 bank per run, {cores} threads, C port of the reference x16 path"
