@@ -150,17 +150,18 @@ int s2_bank_set_pipeline(s2_bank* bank, int n_sub);
 int s2_bank_join(s2_bank* bank, void* stream);
 
 /*
- * Time-split mode for narrow banks (BASELINE config 2: 1,024 voices, 4,096-frame buffers, one-pole filter).
+ * Time-split mode for narrow banks (BASELINE config 2: 1,024 voices, 4,096-frame buffers).
  * With one voice per lane a bank of a thousand voices leaves most of the GPU idle; enable = 1 lets blocks
  * whose voices all hold one period and one cutoff (no pitch modulation, mod envelope at rest or unused by
  * the cutoff) and whose length is a multiple of 1,024 frames render as 32 time segments per voice: the
  * oscillator phase is stepped alone and exactly (try3/oscillators.rs:377-381, bit-exact as always), the
- * one-pole filter state (try3/filters.rs:15-34) enters each segment through a prefix scan of the segments'
- * affine maps.  Output differs from the one-lane-per-voice render only by that scan's reassociation (north
- * star tolerance), so, unlike the default path, a block is not bit-identical to the same frames rendered as
- * two half blocks.  Blocks that do not qualify (and every bus / trace request) take the default path;
- * s2_bank_time_split_blocks counts the blocks that did.  One-pole banks of at most 16,384 voices only;
- * exclusive with s2_bank_set_pipeline(n_sub > 1).
+ * filter state — one-pole `last` (try3/filters.rs:15-34) or the (y1, y2) of the second-order low-pass
+ * (try3/dsp_filters.rs:116-128) — enters each segment through a prefix scan of the segments' affine maps.
+ * Output differs from the one-lane-per-voice render only by that scan's reassociation (north star
+ * tolerance), so, unlike the default path, a block is not bit-identical to the same frames rendered as two
+ * half blocks.  Blocks that do not qualify (and every bus / trace request) take the default path;
+ * s2_bank_time_split_blocks counts the blocks that did.  Banks of at most 16,384 voices only; exclusive
+ * with s2_bank_set_pipeline(n_sub > 1).
  */
 int s2_bank_set_time_split(s2_bank* bank, int enable);
 int s2_bank_time_split_blocks(s2_bank* bank, uint64_t* blocks);

@@ -105,7 +105,7 @@ class VoiceBank:
         check(lib().s2_bank_set_pipeline(self._h, int(n_sub)))
 
     def set_time_split(self, enable: bool = True):
-        """Narrow one-pole banks: render qualifying blocks as 32 time segments per voice (s2_cuda.h)."""
+        """Narrow banks: render qualifying blocks as 32 time segments per voice (s2_cuda.h)."""
         check(lib().s2_bank_set_time_split(self._h, 1 if enable else 0))
 
     @property

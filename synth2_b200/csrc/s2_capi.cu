@@ -181,7 +181,7 @@ struct s2_bank {
     bool ts_enabled = false;
     bool ts_main_dirty = true;            // b->stream carries state writes the pre-pass stream has not seen
     cudaStream_t ts = nullptr;
-    float* d_seg_phase[kTsBufs] = {};     // [n_voices][32] segment-start phases of block p
+    float* d_seg_phase[kTsBufs] = {};     // [n_voices][3][32] segment-start phases (and the two before) of block p
     cudaEvent_t ev_k1[kTsBufs] = {}, ev_k2[kTsBufs] = {}, ev_main = nullptr;
     uint64_t ts_step = 0, ts_blocks = 0;  // ts_blocks: blocks rendered through the time-split kernels
     std::vector<s2_voice_desc> descs;     // host copy of the voice descriptions (banks <= kTsMaxVoices only)
@@ -292,7 +292,7 @@ float host_ms_as_samples(float ms, float sr) { return sr * (ms / 1000.0f); }
 // cutoff for the whole block: no pitch modulation, and the mod envelope either unused by the cutoff or
 // resting (sustain / end) until the block ends.  Conservative: anything unsure renders the general way.
 bool ts_block_eligible(const s2_bank* b, size_t frames, const float* d_voice_out, const float* d_bus_out) {
-    if (!b->ts_enabled || b->filter_kind != S2_FILTER_ONE_POLE || !d_voice_out || d_bus_out) return false;
+    if (!b->ts_enabled || !d_voice_out || d_bus_out) return false;
     if (frames < 1024 || (frames & 1023u) != 0 || frames > (1u << 24)) return false;   // 32 segments of whole chunks
     const float sr = (float)b->sample_rate;
     for (size_t i = 0; i < b->n_voices; i++) {
@@ -344,7 +344,7 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     CUDA_TRY(s2::launch_ts_phase(a, b->d_seg_phase[p], b->ts));
     CUDA_TRY(cudaEventRecord(b->ev_k1[p], b->ts));
     CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_k1[p], 0));
-    CUDA_TRY(s2::launch_ts_render(a, b->d_seg_phase[p], b->stream));
+    CUDA_TRY(s2::launch_ts_render(a, b->filter_kind, b->d_seg_phase[p], b->stream));
     CUDA_TRY(cudaEventRecord(b->ev_k2[p], b->stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);
     b->ts_step++;
@@ -784,14 +784,12 @@ int s2_bank_set_time_split(s2_bank* b, int enable) {
     CUDA_TRY(cudaSetDevice(b->device));
     { int rc = s2_bank_sync(b); if (rc) return rc; }
     if (!enable) { b->ts_enabled = false; return S2_OK; }
-    if (b->filter_kind != S2_FILTER_ONE_POLE)
-        return fail(S2_ERR_INVALID, "time-split rendering composes the one-pole filter's affine state map; this bank uses the biquad");
     if (b->n_voices > kTsMaxVoices)
         return fail(S2_ERR_INVALID, "time-split rendering is for narrow banks (<= %zu voices)", kTsMaxVoices);
     if (b->n_sub > 1) return fail(S2_ERR_INVALID, "time-split and pipelined voice ranges are exclusive");
     if (!b->ts) CUDA_TRY(cudaStreamCreateWithFlags(&b->ts, cudaStreamNonBlocking));
     for (int i = 0; i < kTsBufs; i++) {
-        if (!b->d_seg_phase[i]) CUDA_TRY(cudaMalloc(&b->d_seg_phase[i], b->n_voices * 32 * sizeof(float)));
+        if (!b->d_seg_phase[i]) CUDA_TRY(cudaMalloc(&b->d_seg_phase[i], b->n_voices * 96 * sizeof(float)));
         if (!b->ev_k1[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_k1[i], cudaEventDisableTiming));
         if (!b->ev_k2[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_k2[i], cudaEventDisableTiming));
     }

@@ -59,11 +59,12 @@ cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, 
 uint32_t render_warps(uint32_t n_voices, int nv);
 // producer/consumer warp pair per 32 voices (s2_kernel_pc.cu); same arguments, one voice per lane
 cudaError_t launch_render_pc(const RenderArgs& a, uint32_t filter_kind, cudaStream_t stream);
-// time-split rendering of narrow one-pole banks (s2_kernel_ts.cu): the phase pre-pass writes the phase at the
-// start of each of the block's 32 time segments to seg_phase[n_voices][32]; the render consumes it.
+// time-split rendering of narrow banks (s2_kernel_ts.cu): the phase pre-pass writes, for each of the block's 32
+// time segments, the phase of its first frame and of the two frames before it to seg_phase[n_voices][3][32];
+// the render consumes it.
 // frames must be a multiple of 1024.
 cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t stream);
-cudaError_t launch_ts_render(const RenderArgs& a, const float* seg_phase, cudaStream_t stream);
+cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, const float* seg_phase, cudaStream_t stream);
 // two kernels; seg_scratch holds bus_segments(n_warps) * frames floats
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
                               float* bus, cudaStream_t stream);

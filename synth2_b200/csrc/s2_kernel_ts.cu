@@ -9,10 +9,13 @@
 //     rounding cannot be reassociated if it is to stay bit-exact: it is stepped sequentially, but ALONE
 //     (3 dependent instructions per frame instead of the whole frame), by `ts_phase_kernel`, which records
 //     the phase at the start of each of the block's 32 time segments;
-//   * the one-pole low-pass y = fma(1-k, u, k*y') (try3/filters.rs:15-34), an affine map of its state:
-//     segment s as a whole is y_out = K*y_in + Y_s with K = k^L and Y_s its zero-state response, and the 32
-//     segment maps of a voice compose by a warp-shuffle prefix scan (the "block-wide parallel prefix scan
-//     over the associative affine state-transition operator" of the north star).
+//   * the filter, an affine map of its state.  One-pole y = fma(1-k, u, k*y') (try3/filters.rs:15-34): segment
+//     s as a whole is y_out = K*y_in + Y_s with K = k^L and Y_s its zero-state response.  Second-order low-pass
+//     (try3/dsp_filters.rs:116-128): the recursive state is Y = (y1, y2), one frame is Y' = M Y + (2a*s, 0)
+//     with M = [[2g, -2b], [1, 0]], so a segment is Y_out = M^L Y_in + Z_s (the delayed inputs x1, x2 are not
+//     state to be scanned: they are the oscillator + noise of the two frames before the segment, recomputed
+//     from their recorded phases).  The 32 segment maps of a voice compose by a warp-shuffle prefix scan (the
+//     "parallel prefix scan over the associative affine / 2x2 state-transition operator" of the north star).
 //
 // `ts_render_kernel`: one warp per voice, lane s = frames [s*L, (s+1)*L) of the block (L = frames / 32).
 // Sweep 1 renders the segment from a zero filter state to get Y_s; the scan gives every lane its true start
@@ -44,13 +47,21 @@ __global__ void __launch_bounds__(32) ts_phase_kernel(const RenderArgs a, float*
     const float d = oc.d;
     float ph = __float_as_uint(S[S_HAS_PHASE * vp]) != 0u ? S[S_PHASE * vp] : 0.0f;      // process.rs:316
     const uint32_t L = a.frames / kSegs;
-    float* __restrict__ out = seg_phase + (size_t)slot * kSegs;
+    // seg_phase[slot][plane][segment]: plane 0 = phase of the segment's first frame, planes 1 / 2 = phase of the
+    // one / two frames before it (the biquad's delayed inputs are recomputed from them)
+    float* __restrict__ out = seg_phase + (size_t)slot * (3 * kSegs);
+    float p1 = 0.0f, p2 = 0.0f;
     for (int s = 0; s < kSegs; s++) {
         out[s] = ph;
+        out[kSegs + s] = p1;
+        out[2 * kSegs + s] = p2;
 #pragma unroll 1
         for (uint32_t j = 0; j < L; j += 8u) {
+            const bool last = j + 8u == L;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
+                if (i == 6) p2 = last ? ph : p2;
+                if (i == 7) p1 = last ? ph : p1;
                 ph = wrap_unit(__fadd_rn(ph, d));            // fmod(phase + d, 1), s2_device.cuh
             }
         }
@@ -59,24 +70,29 @@ __global__ void __launch_bounds__(32) ts_phase_kernel(const RenderArgs a, float*
     S[S_HAS_PHASE * vp] = __uint_as_float(1u);
 }
 
-template <int KIND, bool GCONST>
-__device__ __forceinline__ void ts_chunk(FastV<1>& F, const EnvP* amp, uint32_t kind, uint32_t rot, uint32_t n,
-                                         float* row, const float* sintab) {
-    chunk_fast_tp<0, KIND, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab);
-}
-
-template <bool GCONST>
+template <int FILTER, bool GCONST>
 __device__ __forceinline__ void ts_chunk_kind(FastV<1>& F, const EnvP* amp, uint32_t kind, uint32_t rot, uint32_t n,
                                               float* row, const float* sintab) {
     switch (kind) {                       // warp-uniform: a warp is one voice
-    case 0: ts_chunk<0, GCONST>(F, amp, kind, rot, n, row, sintab); break;
-    case 1: ts_chunk<1, GCONST>(F, amp, kind, rot, n, row, sintab); break;
-    case 2: ts_chunk<2, GCONST>(F, amp, kind, rot, n, row, sintab); break;
-    default: ts_chunk<3, GCONST>(F, amp, kind, rot, n, row, sintab); break;
+    case 0: chunk_fast_tp<FILTER, 0, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
+    case 1: chunk_fast_tp<FILTER, 1, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
+    case 2: chunk_fast_tp<FILTER, 2, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
+    default: chunk_fast_tp<FILTER, 3, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
     }
 }
 
+// 2x2 real matrices (row-major) in binary64 for the biquad's segment maps
+struct M22 { double a, b, c, d; };
+__device__ __forceinline__ M22 mul(const M22& x, const M22& y) {       // x * y
+    return {fma(x.a, y.a, x.b * y.c), fma(x.a, y.b, x.b * y.d), fma(x.c, y.a, x.d * y.c), fma(x.c, y.b, x.d * y.d)};
+}
+__device__ __forceinline__ M22 shfl_up(const M22& m, int off) {
+    return {__shfl_up_sync(0xffffffffu, m.a, off), __shfl_up_sync(0xffffffffu, m.b, off),
+            __shfl_up_sync(0xffffffffu, m.c, off), __shfl_up_sync(0xffffffffu, m.d, off)};
+}
+
 // K2: one warp per voice slot; lane = time segment.
+template <int FILTER>
 __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const float* __restrict__ seg_phase) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;                                      // [32 segments][kTileStride]
@@ -110,7 +126,6 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     make_env(M, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
     float* __restrict__ S = a.state + slot;
     const uint32_t n0 = __float_as_uint(S[S_OFFSET * vp]);
-    const float last = S[S_LAST * vp];
 
     // constants of the block: the host admitted this voice because its period and cutoff do not move
     const float amt_lpf = P[P_AMT_LPF * vp];
@@ -119,46 +134,91 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     OscC oc;
     FiltC fc;
     make_osc(oc, P[P_PITCH * vp], sr);
-    make_filt<0>(fc, fl, P[P_DAMP * vp], sr);
+    make_filt<FILTER>(fc, fl, P[P_DAMP * vp], sr);
 
     FastV<1> F;
     F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
     F.gain = P[P_GAIN * vp]; F.namt = P[P_NOISE * vp];
-    F.c0 = fc.c0; F.c1 = fc.c1; F.c2 = fc.c2;
+    F.c0 = fc.c0; F.c1 = FILTER == 0 ? fc.c1 : -fc.c1; F.c2 = fc.c2;       // biquad: the loop adds -2*beta*y2
     F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f;
-    F.x1 = 0.0f; F.x2 = 0.0f; F.y2 = 0.0f;
-    const float ph0 = seg_phase[(size_t)slot * kSegs + lane];
+    const float* __restrict__ sp = seg_phase + (size_t)slot * (3 * kSegs);
+    const float ph0 = sp[lane];
     const uint32_t nl = n0 + (uint32_t)lane * L;             // this lane's first frame offset
     float* row = tile + lane * kTileStride;
     __syncwarp();
 
-    // ---- sweep 1: zero-state response of the segment (gain and output are irrelevant)
-    F.ph = ph0;
-    F.y1 = 0.0f;
-    for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<true>(F, &A, kind, rot, nl + c, row, sintab);
-    const float Yseg = F.y1;
-
-    // ---- the segment maps y -> K*y + Y compose left to right: inclusive Hillis-Steele scan over the lanes
-    float Kc = (float)exp((double)L * log((double)fc.c0));   // k^L (one value per voice)
-    float Yc = Yseg;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float Kp = __shfl_up_sync(0xffffffffu, Kc, off);
-        const float Yp = __shfl_up_sync(0xffffffffu, Yc, off);
-        if (lane >= off) {                                    // (Kp, Yp) happens first, then (Kc, Yc)
-            Yc = __fmaf_rn(Kc, Yp, Yc);
-            Kc = __fmul_rn(Kc, Kp);
+    // delayed inputs of the biquad at the segment start: carried state for segment 0, otherwise the
+    // oscillator + noise of the two frames before the segment (process.rs:341-358 on their recorded phases)
+    float x1_in = 0.0f, x2_in = 0.0f;
+    if (FILTER == 1) {
+        if (lane == 0) { x1_in = S[S_X1 * vp]; x2_in = S[S_X2 * vp]; }
+        else {
+            float pa = sp[kSegs + lane], pb = sp[2 * kSegs + lane];
+            const float oa = osc_step<-1, false>(kind, oc, pa, sintab);
+            const float ob = osc_step<-1, false>(kind, oc, pb, sintab);
+            x1_in = __fadd_rn(__fadd_rn(oa, F.gain), __fadd_rn(noise_fast(rot, nl - 1u), F.namt));
+            x2_in = __fadd_rn(__fadd_rn(ob, F.gain), __fadd_rn(noise_fast(rot, nl - 2u), F.namt));
         }
     }
-    const float end_state = __fmaf_rn(Kc, last, Yc);          // state after this lane's segment
-    float y_in = __shfl_up_sync(0xffffffffu, end_state, 1);
-    if (lane == 0) y_in = last;
+
+    // ---- sweep 1: zero-state response of the segment (gain and output are irrelevant)
+    F.ph = ph0;
+    F.x1 = x1_in; F.x2 = x2_in; F.y1 = 0.0f; F.y2 = 0.0f;
+    for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, kind, rot, nl + c, row, sintab);
+
+    // ---- the segment maps compose left to right: inclusive Hillis-Steele scan over the lanes
+    float y1_in, y2_in = 0.0f;
+    if (FILTER == 0) {
+        const float last = S[S_LAST * vp];
+        float Kc = (float)exp((double)L * log((double)fc.c0));   // k^L (one value per voice)
+        float Yc = F.y1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float Kp = __shfl_up_sync(0xffffffffu, Kc, off);
+            const float Yp = __shfl_up_sync(0xffffffffu, Yc, off);
+            if (lane >= off) {                                // (Kp, Yp) happens first, then (Kc, Yc)
+                Yc = __fmaf_rn(Kc, Yp, Yc);
+                Kc = __fmul_rn(Kc, Kp);
+            }
+        }
+        const float end_state = __fmaf_rn(Kc, last, Yc);      // state after this lane's segment
+        y1_in = __shfl_up_sync(0xffffffffu, end_state, 1);
+        if (lane == 0) y1_in = last;
+    } else {
+        // one frame: (y1, y2)' = M (y1, y2) + (2a*s, 0),  M = [[2g, -2b], [1, 0]]  (filt_step<1>)
+        M22 Mc = {1.0, 0.0, 0.0, 1.0};
+        {
+            M22 base = {(double)fc.c2, -(double)fc.c1, 1.0, 0.0};
+            for (uint32_t e = L; e; e >>= 1) {                // M^L by squaring
+                if (e & 1u) Mc = mul(base, Mc);
+                base = mul(base, base);
+            }
+        }
+        double z1 = (double)F.y1, z2 = (double)F.y2;          // zero-state response of this segment
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const M22 Mp = shfl_up(Mc, off);
+            const double p1 = __shfl_up_sync(0xffffffffu, z1, off), p2 = __shfl_up_sync(0xffffffffu, z2, off);
+            if (lane >= off) {                                // earlier map (Mp, p) first, then (Mc, z)
+                const double n1 = fma(Mc.a, p1, fma(Mc.b, p2, z1));
+                const double n2 = fma(Mc.c, p1, fma(Mc.d, p2, z2));
+                z1 = n1; z2 = n2;
+                Mc = mul(Mc, Mp);
+            }
+        }
+        const double y10 = (double)S[S_Y1 * vp], y20 = (double)S[S_Y2 * vp];
+        const double e1 = fma(Mc.a, y10, fma(Mc.b, y20, z1));    // state after this lane's segment
+        const double e2 = fma(Mc.c, y10, fma(Mc.d, y20, z2));
+        const double u1 = __shfl_up_sync(0xffffffffu, e1, 1), u2 = __shfl_up_sync(0xffffffffu, e2, 1);
+        y1_in = lane == 0 ? (float)y10 : (float)u1;
+        y2_in = lane == 0 ? (float)y20 : (float)u2;
+    }
 
     // ---- sweep 2: the reference recurrence from the true start state, written out
     F.ph = ph0;
-    F.y1 = y_in;
+    F.x1 = x1_in; F.x2 = x2_in; F.y1 = y1_in; F.y2 = y2_in;
     for (uint32_t c = 0; c < L; c += kChunk) {
-        ts_chunk_kind<false>(F, &A, kind, rot, nl + c, row, sintab);
+        ts_chunk_kind<FILTER, false>(F, &A, kind, rot, nl + c, row, sintab);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -169,7 +229,8 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
         __syncwarp();
     }
     if (lane == 31) {
-        S[S_LAST * vp] = F.y1;
+        if (FILTER == 0) S[S_LAST * vp] = F.y1;
+        else { S[S_X1 * vp] = F.x1; S[S_X2 * vp] = F.x2; S[S_Y1 * vp] = F.y1; S[S_Y2 * vp] = F.y2; }
         S[S_OFFSET * vp] = __uint_as_float(n0 + frames);      // n0 + frames <= 2^24 (host check)
     }
 }
@@ -182,10 +243,11 @@ cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_ts_render(const RenderArgs& a, const float* seg_phase, cudaStream_t stream) {
+cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, const float* seg_phase, cudaStream_t stream) {
     if (a.n_voices == 0) return cudaSuccess;
     const size_t smem = (32 * kTileStride + 1024) * sizeof(float);
-    ts_render_kernel<<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    if (filter_kind == 0) ts_render_kernel<0><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    else ts_render_kernel<1><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,24 @@ def config2(stream):
         bank.close()
 
 
+def config2_biquad(stream):
+    """Config 2's shape with the resonant low-pass: the 2x2 scan of the time-split kernels."""
+    V, T, blocks = 1024, 4096, 256
+    voices = bankgen.make_bank(V, 4 * blocks * T, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
+    for time_split in (False, True):
+        bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=0, stream=stream)
+        if time_split:
+            bank.set_time_split(True)
+        ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
+        for i in range(16):
+            bank.render(T, ring[i & 15], T, None)
+        n0 = bank.time_split_blocks
+        sec = timed(stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
+        report("2b: 1,024 saw/square + biquad, 4,096-frame buffers, sustain" + (", time-split" if time_split else ", one voice per lane"),
+               V, blocks * T, sec, blocks=blocks, us_per_block=sec / blocks * 1e6, time_split_blocks=bank.time_split_blocks - n0)
+        bank.close()
+
+
 def config4(stream):
     V, T, blocks = 32768, 4096, 118            # 10 s
     voices = bankgen.make_bank(V, blocks * T, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
@@ -119,8 +137,8 @@ def config5(stream):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["2", "4", "5"]
+    which = sys.argv[1:] or ["2", "2b", "4", "5"]
     torch.cuda.set_device(0)
     stream = torch.cuda.current_stream()
     for w in which:
-        {"2": config2, "4": config4, "5": config5}[w](stream)
+        {"2": config2, "2b": config2_biquad, "4": config4, "5": config5}[w](stream)
