@@ -39,8 +39,14 @@ enum { S2_OSC_SQUARE = 0, S2_OSC_SAW = 1, S2_OSC_TRIANGLE = 2, S2_OSC_SINE = 3 }
 
 /* Voice filter.  ONE_POLE is the live reference filter (filters.rs:15-34, driven per sample at
    process.rs:363-371).  BIQUAD_LP is `SecondOrderLowPassFilter` (dsp_filters.rs:82-130), which
-   the reference declares but never calls; it is offered for BASELINE config 3. */
-enum { S2_FILTER_ONE_POLE = 0, S2_FILTER_BIQUAD_LP = 1 };
+   the reference declares but never calls; it is offered for BASELINE config 3.  The rest of that file
+   (equally uncalled in the reference): BIQUAD_HP = `SecondOrderHighPassFilter`
+   (dsp_filters.rs:132-178), BIQUAD_BP = `SecondOrderBandPassFilter` (:180-230; the voice's `damping` field
+   carries its quality factor, `lpf_freq_hz` its centre frequency), FIRST_ORDER_LP / _HP =
+   `FirstOrderLowPassFilter` / `FirstOrderHighPassFilter` (:12-80; `damping` unused).  In every case the
+   cutoff follows the mod envelope exactly as the low-pass's does (process.rs:148-152). */
+enum { S2_FILTER_ONE_POLE = 0, S2_FILTER_BIQUAD_LP = 1, S2_FILTER_BIQUAD_HP = 2, S2_FILTER_BIQUAD_BP = 3,
+       S2_FILTER_FIRST_ORDER_LP = 4, S2_FILTER_FIRST_ORDER_HP = 5 };
 
 #define S2_NO_RELEASE 0xFFFFFFFFu /* release_frame_offset == None (synth.rs:28; simdtest.rs:283) */
 
@@ -161,7 +167,7 @@ int s2_bank_join(s2_bank* bank, void* stream);
  * tolerance), so, unlike the default path, a block is not bit-identical to the same frames rendered as two
  * half blocks.  Blocks that do not qualify (and every bus / trace request) take the default path;
  * s2_bank_time_split_blocks counts the blocks that did.  Banks of at most 16,384 voices only; exclusive
- * with s2_bank_set_pipeline(n_sub > 1).
+ * with s2_bank_set_pipeline(n_sub > 1); filter kinds ONE_POLE and BIQUAD_LP.
  */
 int s2_bank_set_time_split(s2_bank* bank, int enable);
 int s2_bank_time_split_blocks(s2_bank* bank, uint64_t* blocks);
@@ -197,7 +203,7 @@ int s2_synth_sample(s2_synth* synth, float* h_buffer, size_t frames, uint32_t sa
  */
 typedef struct s2_patch {
     s2_voice_desc voice;     /* static_config::Layer as a voice template: pitch/offsets/active are ignored */
-    uint32_t filter_kind;    /* S2_FILTER_ONE_POLE (the reference's live path) or S2_FILTER_BIQUAD_LP */
+    uint32_t filter_kind;    /* S2_FILTER_ONE_POLE (the reference's live path) or another S2_FILTER_* */
     char name[60];           /* `synth NAME { ... }` */
 } s2_patch;                  /* 144 bytes */
 

@@ -315,11 +315,91 @@ float s2o_biquad_lp_process(s2o_layer_state* st, uint32_t sample_rate, float cut
     return y;
 }
 
+/* s2_lib/src/try3/dsp_filters.rs:132-178 SecondOrderHighPassFilter::process */
+float s2o_biquad_hp_process(s2o_layer_state* st, uint32_t sample_rate, float cutoff, float damping,
+                            float input) {
+    float sr = (float)sample_rate;
+    float pi = 3.14159274101257324219f;
+    float theta = 2.0f * pi;
+    theta = theta * cutoff;
+    theta = theta / sr;
+    float sn = sinf(theta);
+    float cs = cosf(theta);
+    float hd = damping / 2.0f;
+    float num = 1.0f - hd * sn;
+    float den = 1.0f + hd * sn;
+    float beta = (1.0f / 2.0f) * (num / den);
+    float gamma = (1.0f / 2.0f + beta) * cs;
+    float alpha = (1.0f / 2.0f + beta + gamma) / 4.0f;
+    float x1 = st->x1, x2 = st->x2, y1 = st->y1, y2 = st->y2;
+    float x = input;
+    float s = x - 2.0f * x1;
+    s = s + x2;
+    float t = alpha * s;
+    t = t + gamma * y1;
+    t = t - beta * y2;
+    float y = 2.0f * t;
+    st->x2 = x1;
+    st->x1 = x;
+    st->y2 = y1;
+    st->y1 = y;
+    return y;
+}
+
+/* s2_lib/src/try3/dsp_filters.rs:180-230 SecondOrderBandPassFilter::process; `quality` = quality_factor */
+float s2o_biquad_bp_process(s2o_layer_state* st, uint32_t sample_rate, float center, float quality,
+                            float input) {
+    float sr = (float)sample_rate;
+    float pi = 3.14159274101257324219f;
+    float theta = 2.0f * pi;
+    theta = theta * center;
+    theta = theta / sr;
+    float tn = tanf(theta / (2.0f * quality));
+    float beta = (1.0f / 2.0f) * ((1.0f - tn) / (1.0f + tn));
+    float gamma = (1.0f / 2.0f + beta) * cosf(theta);
+    float alpha = (1.0f / 2.0f - beta) / 2.0f;
+    float x2 = st->x2, y1 = st->y1, y2 = st->y2, x1 = st->x1;
+    float x = input;
+    float t = alpha * (x - x2);
+    t = t + gamma * y1;
+    t = t - beta * y2;
+    float y = 2.0f * t;
+    st->x2 = x1;
+    st->x1 = x;
+    st->y2 = y1;
+    st->y1 = y;
+    return y;
+}
+
+/* s2_lib/src/try3/dsp_filters.rs:12-44 FirstOrderLowPassFilter::process (high = 0) and :46-80
+   FirstOrderHighPassFilter::process (high = 1) */
+float s2o_first_order_process(s2o_layer_state* st, uint32_t sample_rate, float cutoff, int high, float input) {
+    float sr = (float)sample_rate;
+    float pi = 3.14159274101257324219f;
+    float theta = 2.0f * pi;
+    theta = theta * cutoff;
+    theta = theta / sr;
+    float gamma = cosf(theta) / (1.0f + sinf(theta));
+    float alpha = high ? (1.0f + gamma) / 2.0f : (1.0f - gamma) / 2.0f;
+    float x1 = st->x1, y1 = st->y1;
+    float x = input;
+    float xs = high ? x - x1 : x + x1;
+    float y = alpha * xs + gamma * y1;
+    st->x1 = x;
+    st->y1 = y;
+    return y;
+}
+
 static float filter_process(const s2o_layer_config* cfg, s2o_layer_state* st, uint32_t sr, float freq,
                             float input) {
-    if (cfg->filter_kind == S2O_FILTER_BIQUAD_LP)
-        return s2o_biquad_lp_process(st, sr, freq, cfg->damping, input);
-    return s2o_lpf_process(&st->lpf_last, sr, freq, input);
+    switch (cfg->filter_kind) {
+    case S2O_FILTER_BIQUAD_LP: return s2o_biquad_lp_process(st, sr, freq, cfg->damping, input);
+    case S2O_FILTER_BIQUAD_HP: return s2o_biquad_hp_process(st, sr, freq, cfg->damping, input);
+    case S2O_FILTER_BIQUAD_BP: return s2o_biquad_bp_process(st, sr, freq, cfg->damping, input);
+    case S2O_FILTER_FIRST_ORDER_LP: return s2o_first_order_process(st, sr, freq, 0, input);
+    case S2O_FILTER_FIRST_ORDER_HP: return s2o_first_order_process(st, sr, freq, 1, input);
+    default: return s2o_lpf_process(&st->lpf_last, sr, freq, input);
+    }
 }
 
 /* ------------------------------------------------------------------ process.rs */

@@ -35,7 +35,8 @@ extern "C" {
 /* static_config.rs:25-31 (declaration order) */
 enum { S2O_OSC_SQUARE = 0, S2O_OSC_SAW = 1, S2O_OSC_TRIANGLE = 2, S2O_OSC_SINE = 3 };
 /* 0: filters.rs:15-34 (live path)   1: dsp_filters.rs:82-130 (spec for "resonant biquad") */
-enum { S2O_FILTER_ONE_POLE = 0, S2O_FILTER_BIQUAD_LP = 1 };
+enum { S2O_FILTER_ONE_POLE = 0, S2O_FILTER_BIQUAD_LP = 1, S2O_FILTER_BIQUAD_HP = 2, S2O_FILTER_BIQUAD_BP = 3,
+       S2O_FILTER_FIRST_ORDER_LP = 4, S2O_FILTER_FIRST_ORDER_HP = 5 };
 
 #define S2O_NO_RELEASE 0xFFFFFFFFu /* Option::None == unwrap_or(u32::MAX): simdtest.rs:283, envelopes.rs:35 */
 
@@ -119,6 +120,10 @@ float s2o_lpf_coeff(float freq, uint32_t sample_rate);             /* filters.rs
 float s2o_lpf_process(float* last, uint32_t sample_rate, float freq, float input); /* filters.rs:15-34 */
 /* coefficients (alpha, beta, gamma) of dsp_filters.rs:99-109 */
 void s2o_biquad_lp_coeffs(uint32_t sample_rate, float cutoff, float damping, float* abg);
+/* dsp_filters.rs:132-230 and :12-80 (dead code in the reference, like the low-pass above) */
+float s2o_biquad_hp_process(s2o_layer_state* st, uint32_t sample_rate, float cutoff, float damping, float input);
+float s2o_biquad_bp_process(s2o_layer_state* st, uint32_t sample_rate, float center, float quality, float input);
+float s2o_first_order_process(s2o_layer_state* st, uint32_t sample_rate, float cutoff, int high, float input);
 float s2o_biquad_lp_process(s2o_layer_state* st, uint32_t sample_rate, float cutoff, float damping,
                             float input);                          /* dsp_filters.rs:91-130 */
 const float* s2o_sin_table(void);                                  /* tables.rs:1-1026 */

@@ -12,7 +12,8 @@ the host-side mirror of the reference interface:
 Importing the package does not need a GPU; creating a Synth / VoiceBank does, and fails loudly
 without one (no CPU or PyTorch fallback exists).
 """
-from ._lib import (FILTER_BIQUAD_LP, FILTER_ONE_POLE, NO_RELEASE, NOTE_EVENT, OSC_SAW, OSC_SINE, OSC_SQUARE,
+from ._lib import (FILTER_BIQUAD_BP, FILTER_BIQUAD_HP, FILTER_BIQUAD_LP, FILTER_FIRST_ORDER_HP, FILTER_FIRST_ORDER_LP,
+                   FILTER_ONE_POLE, NO_RELEASE, NOTE_EVENT, OSC_SAW, OSC_SINE, OSC_SQUARE,
                    OSC_TRIANGLE, PATCH, VOICE_DESC, VOICE_STATE, S2Error, lib)
 from . import patch
 from .bank import VoiceBank, default_voice, note_to_pitch
@@ -22,5 +23,6 @@ from .synth import FrameOffset, Note, Synth, Velocity
 __all__ = [
     "Synth", "Player", "Note", "Velocity", "FrameOffset", "VoiceBank", "default_voice", "note_to_pitch",
     "VOICE_DESC", "VOICE_STATE", "PATCH", "NOTE_EVENT", "patch", "S2Error", "lib", "NO_RELEASE",
-    "OSC_SQUARE", "OSC_SAW", "OSC_TRIANGLE", "OSC_SINE", "FILTER_ONE_POLE", "FILTER_BIQUAD_LP",
+    "OSC_SQUARE", "OSC_SAW", "OSC_TRIANGLE", "OSC_SINE", "FILTER_ONE_POLE", "FILTER_BIQUAD_LP", "FILTER_BIQUAD_HP", "FILTER_BIQUAD_BP", "FILTER_FIRST_ORDER_LP",
+    "FILTER_FIRST_ORDER_HP",
 ]

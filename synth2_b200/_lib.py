@@ -20,6 +20,7 @@ S2_ERR_NOMEM = -5
 
 OSC_SQUARE, OSC_SAW, OSC_TRIANGLE, OSC_SINE = 0, 1, 2, 3
 FILTER_ONE_POLE, FILTER_BIQUAD_LP = 0, 1
+FILTER_BIQUAD_HP, FILTER_BIQUAD_BP, FILTER_FIRST_ORDER_LP, FILTER_FIRST_ORDER_HP = 2, 3, 4, 5
 NO_RELEASE = 0xFFFFFFFF
 
 # struct s2_voice_desc (80 bytes) / s2_voice_state (32 bytes), include/s2_cuda.h

@@ -469,7 +469,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     if (n_voices == 0 || !voices) return fail(S2_ERR_INVALID, "empty bank");
     if (n_voices > 0x7FFFFFE0ull) return fail(S2_ERR_INVALID, "too many voices");
     if (sample_rate == 0) return fail(S2_ERR_INVALID, "sample_rate must be > 0");
-    if (filter_kind > S2_FILTER_BIQUAD_LP) return fail(S2_ERR_INVALID, "filter_kind %u", filter_kind);
+    if (filter_kind > S2_FILTER_FIRST_ORDER_HP) return fail(S2_ERR_INVALID, "filter_kind %u", filter_kind);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(S2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
@@ -497,6 +497,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
         if (f[0] == '1') b->nv = 1;
         if (f[0] == '2') { b->nv = 2; b->pc = false; }
     }
+    if (filter_kind > S2_FILTER_BIQUAD_LP) { b->nv = 1; b->pc = false; }   // the experimental layouts know two filters
 
     b->voice_of_slot.resize(n_voices);
     b->slot_of_voice.resize(n_voices);
@@ -784,6 +785,8 @@ int s2_bank_set_time_split(s2_bank* b, int enable) {
     CUDA_TRY(cudaSetDevice(b->device));
     { int rc = s2_bank_sync(b); if (rc) return rc; }
     if (!enable) { b->ts_enabled = false; return S2_OK; }
+    if (b->filter_kind > S2_FILTER_BIQUAD_LP)
+        return fail(S2_ERR_INVALID, "time-split rendering knows the one-pole and the second-order low-pass filters");
     if (b->n_voices > kTsMaxVoices)
         return fail(S2_ERR_INVALID, "time-split rendering is for narrow banks (<= %zu voices)", kTsMaxVoices);
     if (b->n_sub > 1) return fail(S2_ERR_INVALID, "time-split and pipelined voice ranges are exclusive");
@@ -979,7 +982,7 @@ int s2_synth_sample(s2_synth* s, float* h_buffer, size_t frames, uint32_t sample
 
 int s2_synth_set_patch(s2_synth* s, const s2_patch* patch) {
     if (!s || !patch) return fail(S2_ERR_INVALID, "null argument");
-    if (patch->filter_kind > S2_FILTER_BIQUAD_LP) return fail(S2_ERR_INVALID, "filter_kind %u", patch->filter_kind);
+    if (patch->filter_kind > S2_FILTER_FIRST_ORDER_HP) return fail(S2_ERR_INVALID, "filter_kind %u", patch->filter_kind);
     s2_voice_desc probe = patch->voice;
     probe.pitch_hz = 440.0f;                    // the template's pitch is replaced per note
     int rc = validate_voice(probe, 0);

@@ -175,6 +175,9 @@ __device__ __forceinline__ void make_osc(OscC& o, float fo, float sr) {
     o.ts2 = __fdiv_rn(2.0f, o.half);
 }
 
+// FILTER template values = S2_FILTER_* of include/s2_cuda.h
+enum { FILT_ONE_POLE = 0, FILT_BIQUAD_LP = 1, FILT_BIQUAD_HP = 2, FILT_BIQUAD_BP = 3, FILT_FIRST_LP = 4, FILT_FIRST_HP = 5 };
+
 template <int FILTER>
 __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float sr) {
     c.fl_bits = __float_as_uint(fl);
@@ -188,8 +191,8 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         c.c0 = k;
         c.c1 = __fsub_rn(1.0f, k);
         c.c2 = 0.0f;
-    } else {
-        // try3/dsp_filters.rs:99-109
+    } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
+        // try3/dsp_filters.rs:99-109 (low-pass), :149-159 (high-pass: alpha = (1/2 + beta + gamma) / 4)
         float th = __fmul_rn(2.0f, pi);
         th = __fmul_rn(th, fl);
         th = __fdiv_rn(th, sr);
@@ -200,12 +203,38 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         const float den = __fadd_rn(1.0f, __fmul_rn(hd, s));
         const float beta = __fmul_rn(0.5f, __fdiv_rn(num, den));
         const float gamma = __fmul_rn(__fadd_rn(0.5f, beta), co);
-        const float alpha = __fmul_rn(__fsub_rn(__fadd_rn(0.5f, beta), gamma), 0.25f);      // ... / 4.0, likewise
+        const float hb = __fadd_rn(0.5f, beta);
+        const float alpha = __fmul_rn(FILTER == FILT_BIQUAD_LP ? __fsub_rn(hb, gamma) : __fadd_rn(hb, gamma), 0.25f);   // ... / 4.0, likewise
         // y = 2*(alpha*s + gamma*y1 - beta*y2): scaling by 2 commutes with round-to-nearest, so the
         // doubling is folded into the coefficients (exact unless an intermediate is subnormal).
         c.c0 = __fmul_rn(2.0f, alpha);
         c.c1 = __fmul_rn(2.0f, beta);
         c.c2 = __fmul_rn(2.0f, gamma);
+    } else if (FILTER == FILT_BIQUAD_BP) {
+        // try3/dsp_filters.rs:197-207; `damp` carries the quality factor
+        float th = __fmul_rn(2.0f, pi);
+        th = __fmul_rn(th, fl);
+        th = __fdiv_rn(th, sr);
+        const float tn = s2_tanf(__fdiv_rn(th, __fmul_rn(2.0f, damp)));
+        const float beta = __fmul_rn(0.5f, __fdiv_rn(__fsub_rn(1.0f, tn), __fadd_rn(1.0f, tn)));
+        float s, co;
+        s2_sincosf(th, &s, &co);
+        const float gamma = __fmul_rn(__fadd_rn(0.5f, beta), co);
+        const float alpha = __fmul_rn(__fsub_rn(0.5f, beta), 0.5f);
+        c.c0 = __fmul_rn(2.0f, alpha);
+        c.c1 = __fmul_rn(2.0f, beta);
+        c.c2 = __fmul_rn(2.0f, gamma);
+    } else {
+        // try3/dsp_filters.rs:30-32 (first-order low-pass) / :64-66 (high-pass): c0 = alpha, c2 = gamma
+        float th = __fmul_rn(2.0f, pi);
+        th = __fmul_rn(th, fl);
+        th = __fdiv_rn(th, sr);
+        float s, co;
+        s2_sincosf(th, &s, &co);
+        const float gamma = __fdiv_rn(co, __fadd_rn(1.0f, s));
+        c.c0 = __fmul_rn(FILTER == FILT_FIRST_LP ? __fsub_rn(1.0f, gamma) : __fadd_rn(1.0f, gamma), 0.5f);
+        c.c1 = 0.0f;
+        c.c2 = gamma;
     }
 }
 
@@ -294,15 +323,23 @@ __device__ __forceinline__ float filt_step(float u, const FiltC& c, FiltS& s) {
         const float y = __fmaf_rn(c.c1, u, __fmul_rn(c.c0, s.y1));
         s.y1 = y;
         return y;
-    } else {
-        // try3/dsp_filters.rs:116-128: 2*(alpha*(x + 2*x1 + x2) + gamma*y1 - beta*y2);
-        // x + 2*x1 is one fma because 2*x1 is exact
-        float sx = __fmaf_rn(2.0f, s.x1, u);
-        sx = __fadd_rn(sx, s.x2);
+    } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP || FILTER == FILT_BIQUAD_BP) {
+        // try3/dsp_filters.rs:116-128: 2*(alpha*(x + 2*x1 + x2) + gamma*y1 - beta*y2); x + 2*x1 is one fma
+        // because 2*x1 is exact.  :166-176 (high-pass) has x - 2*x1 + x2, :214-224 (band-pass) x - x2.
+        float sx;
+        if (FILTER == FILT_BIQUAD_LP) sx = __fadd_rn(__fmaf_rn(2.0f, s.x1, u), s.x2);
+        else if (FILTER == FILT_BIQUAD_HP) sx = __fadd_rn(__fmaf_rn(-2.0f, s.x1, u), s.x2);
+        else sx = __fsub_rn(u, s.x2);
         float t = __fmul_rn(c.c0, sx);
         t = __fadd_rn(t, __fmul_rn(c.c2, s.y1));
         t = __fsub_rn(t, __fmul_rn(c.c1, s.y2));
         s.x2 = s.x1; s.x1 = u; s.y2 = s.y1; s.y1 = t;
+        return t;
+    } else {
+        // try3/dsp_filters.rs:37-41 / :71-75: alpha * (x +- x1) + gamma * y1 (no mul_add in the source)
+        const float xs = FILTER == FILT_FIRST_LP ? __fadd_rn(u, s.x1) : __fsub_rn(u, s.x1);
+        const float t = __fadd_rn(__fmul_rn(c.c0, xs), __fmul_rn(c.c2, s.y1));
+        s.x1 = u; s.y1 = t;
         return t;
     }
 }

@@ -531,16 +531,23 @@ static cudaError_t launch_t(const RenderArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int NV>
-static cudaError_t launch_nv(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream) {
-    if (filter_kind == 0)
-        return trace == TRACE_PHASE ? launch_t<NV, 0, TRACE_PHASE>(a, stream) : launch_t<NV, 0, TRACE_NONE>(a, stream);
-    return trace == TRACE_PHASE ? launch_t<NV, 1, TRACE_PHASE>(a, stream) : launch_t<NV, 1, TRACE_NONE>(a, stream);
+template <int NV, int FILTER>
+static cudaError_t launch_f(const RenderArgs& a, int trace, cudaStream_t stream) {
+    return trace == TRACE_PHASE ? launch_t<NV, FILTER, TRACE_PHASE>(a, stream) : launch_t<NV, FILTER, TRACE_NONE>(a, stream);
 }
 
 cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, int nv, cudaStream_t stream) {
     if (a.n_voices == 0 || a.frames == 0) return cudaSuccess;
-    return nv == 2 ? launch_nv<2>(a, filter_kind, trace, stream) : launch_nv<1>(a, filter_kind, trace, stream);
+    switch (filter_kind) {
+    case FILT_ONE_POLE: return nv == 2 ? launch_f<2, FILT_ONE_POLE>(a, trace, stream) : launch_f<1, FILT_ONE_POLE>(a, trace, stream);
+    case FILT_BIQUAD_LP: return nv == 2 ? launch_f<2, FILT_BIQUAD_LP>(a, trace, stream) : launch_f<1, FILT_BIQUAD_LP>(a, trace, stream);
+    // the remaining dsp_filters.rs filters: one voice per lane only
+    case FILT_BIQUAD_HP: return launch_f<1, FILT_BIQUAD_HP>(a, trace, stream);
+    case FILT_BIQUAD_BP: return launch_f<1, FILT_BIQUAD_BP>(a, trace, stream);
+    case FILT_FIRST_LP: return launch_f<1, FILT_FIRST_LP>(a, trace, stream);
+    case FILT_FIRST_HP: return launch_f<1, FILT_FIRST_HP>(a, trace, stream);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 uint32_t bus_segments(uint32_t n_warps) { return (n_warps + kBusSegWarps - 1) / kBusSegWarps; }

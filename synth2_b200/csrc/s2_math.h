@@ -1,4 +1,4 @@
-// s2_math.h — the three transcendentals of the render path (2^x, e^x, sin/cos), evaluated in binary64 and
+// s2_math.h — the transcendentals of the render path (2^x, e^x, sin/cos, tan), evaluated in binary64 and
 // rounded once to binary32.
 //
 // The reference calls sleef `pow(2, x)` (process.rs:244), libm `powf` (process.rs:227), `expf`
@@ -110,9 +110,8 @@ S2_HD float s2_expf(float x) {
     return (float)s2_scale2(s2_exp_kernel(r), k);
 }
 
-// sin and cos of x (binary32, |x| < ~1e5) — one reduction, two Taylor kernels on |r| <= pi/4.
-S2_HD void s2_sincosf(float x, float* s, float* c) {
-    const double xd = (double)x;
+// sin and cos of x (|x| < ~1e5) in binary64 — one reduction, two Taylor kernels on |r| <= pi/4.
+S2_HD void s2_sincos_d(double xd, double* s, double* c) {
     int qi;
     const double qd = s2_rint_int(xd * S2K(S2K_TWO_OVER_PI), &qi);          // x * 2/pi
     // pi/2 = pio2_1 + pio2_1t (+ 2e-21): pio2_1 has 33 significant bits, so qd * pio2_1 is exact
@@ -140,6 +139,21 @@ S2_HD void s2_sincosf(float x, float* s, float* c) {
     const int q = qi & 3;
     const double sv = (q & 1) ? cr : sr;
     const double cv = (q & 1) ? sr : cr;
-    *s = (float)((q & 2) ? -sv : sv);
-    *c = (float)(((q + 1) & 2) ? -cv : cv);
+    *s = (q & 2) ? -sv : sv;
+    *c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// sin and cos of a binary32 x, each rounded once
+S2_HD void s2_sincosf(float x, float* s, float* c) {
+    double sd, cd;
+    s2_sincos_d((double)x, &sd, &cd);
+    *s = (float)sd;
+    *c = (float)cd;
+}
+
+// tan of a binary32 x: sin / cos in binary64 (relative error ~3e-16), rounded once
+S2_HD float s2_tanf(float x) {
+    double sd, cd;
+    s2_sincos_d((double)x, &sd, &cd);
+    return (float)(sd / cd);
 }

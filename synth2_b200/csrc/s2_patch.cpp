@@ -15,7 +15,8 @@
 //   synth lead {
 //       osc { kind saw; gain 1.0 }              # kind: square | saw | triangle | sine
 //       noise 0.0
-//       lpf { freq 200; kind one_pole }         # kind: one_pole (filters.rs) | biquad (dsp_filters.rs:82-130); damping 1.414
+//       lpf { freq 200; kind one_pole }         # kind: one_pole (filters.rs) | biquad | biquad_hp | biquad_bp |
+//                                               #       first_order | first_order_hp (dsp_filters.rs); damping 1.414
 //       amp_env { attack 100; decay 100; sustain 0.5; release 100 }          # Ms, Ms, Unipolar<1>, Ms
 //       mod_env { attack 0; decay 200; sustain 0; release 0 }
 //       modulations { mod_env_to_osc_freq 0; mod_env_to_lpf_freq 10 }        # Bipolar<10>
@@ -196,6 +197,10 @@ struct Parser {
                         if (t.kind != Tok::Name) return err("lpf.kind: expected one_pole or biquad");
                         if (t.text == "one_pole") out->filter_kind = S2_FILTER_ONE_POLE;
                         else if (t.text == "biquad") out->filter_kind = S2_FILTER_BIQUAD_LP;
+                        else if (t.text == "biquad_hp") out->filter_kind = S2_FILTER_BIQUAD_HP;
+                        else if (t.text == "biquad_bp") out->filter_kind = S2_FILTER_BIQUAD_BP;       // damping = quality factor
+                        else if (t.text == "first_order") out->filter_kind = S2_FILTER_FIRST_ORDER_LP;
+                        else if (t.text == "first_order_hp") out->filter_kind = S2_FILTER_FIRST_ORDER_HP;
                         else return err("lpf.kind: unknown filter '%s'", t.text.c_str());
                         if (!advance()) return false;
                     } else return err("unknown field lpf.%s", g.c_str());

@@ -42,6 +42,10 @@ _SIGS = {
     "s2o_lpf_coeff": (_f, [_f, _u32]),
     "s2o_lpf_process": (_f, [_vp, _u32, _f, _f]),
     "s2o_biquad_lp_coeffs": (None, [_u32, _f, _f, _vp]),
+    "s2o_biquad_lp_process": (_f, [_vp, _u32, _f, _f, _f]),
+    "s2o_biquad_hp_process": (_f, [_vp, _u32, _f, _f, _f]),
+    "s2o_biquad_bp_process": (_f, [_vp, _u32, _f, _f, _f]),
+    "s2o_first_order_process": (_f, [_vp, _u32, _f, _i, _f]),
     "s2o_sin_table": (_vp, []),
     "s2o_process_layer_x16": (None, [_vp, _vp, _f, _u32, _u32, _u32, _vp]),
     "s2o_process_layer": (_f, [_vp, _vp, _f, _u32, _u32, _u32]),

@@ -900,3 +900,52 @@ def test_no_write_outside_the_output_rows(mode, V, frames):
     assert np.all(b[:32] == -777.0) and np.all(b[32 + frames:] == -777.0)
     if mode != "time_split":
         assert not np.any(b[32:32 + frames] == -777.0)
+
+
+# ------------------------------------------------------------------------------ the rest of dsp_filters.rs
+
+@pytest.mark.parametrize("filter_kind", [s2.FILTER_BIQUAD_HP, s2.FILTER_BIQUAD_BP, s2.FILTER_FIRST_ORDER_LP,
+                                         s2.FILTER_FIRST_ORDER_HP])
+def test_remaining_dsp_filters_against_oracle(filter_kind):
+    """SecondOrderHighPass / SecondOrderBandPass / FirstOrderLowPass / FirstOrderHighPass (dsp_filters.rs:12-80,
+    132-230) as the voice filter: sustain, moving cutoff, ramps, ragged blocks and the bus, against the oracle."""
+    V = 96
+    blocks = [4096, 4096, 2048, 1000, 3096]
+    v = bankgen.make_bank(V, sum(blocks), kinds=(s2.OSC_SAW, s2.OSC_SQUARE, s2.OSC_TRIANGLE, s2.OSC_SINE),
+                          mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
+    v["noise_amt"][::3] = 0.25
+    if filter_kind == s2.FILTER_BIQUAD_BP:
+        v["damping"] += 2.0        # the field is the quality factor here; theta / (2 Q) must stay below pi / 4
+    ref, rbus, rst = oracle_bank_render(v, filter_kind, blocks)
+    assert np.all(np.isfinite(ref))
+    got, gbus, st = gpu_bank_render(v, filter_kind, blocks)
+    assert_parity(ref, got, f"filter kind {filter_kind}")
+    assert st["phase"].tobytes() == rst["phase"].tobytes()
+    for k in ("x1", "y1") + (("x2", "y2") if filter_kind in (s2.FILTER_BIQUAD_HP, s2.FILTER_BIQUAD_BP) else ()):
+        np.testing.assert_allclose(st[k], rst[k], atol=TOL_ABS * 4, rtol=0)
+    scale = max(1.0, float(np.max(np.abs(rbus))))
+    assert float(np.max(np.abs(gbus - rbus))) <= TOL_ABS * scale
+    # pipelined voice ranges give the same bits
+    with s2.VoiceBank(v, SR, filter_kind) as bank:
+        bank.set_pipeline(2)
+        out = torch.empty((V, 4096), device="cuda", dtype=torch.float32)
+        bank.render(4096, out, 4096, None)
+        bank.sync()
+        assert out.cpu().numpy().tobytes() == got[:, :4096].tobytes()
+        with pytest.raises(s2.S2Error):
+            bank.set_time_split(True)
+
+
+def test_patch_selects_the_remaining_filters():
+    p = s2patch.parse("synth hp { osc { kind saw } lpf { freq 700; kind biquad_hp; damping 0.9 } "
+                      "mod_env { decay 0 } modulations { mod_env_to_lpf_freq 0 } } score { on 0 60; off 9600 60 }")
+    assert p.filter_kind == s2.FILTER_BIQUAD_HP
+    syn = s2.Synth()
+    syn.set_patch(p)
+    got = syn.render_score(p.events, 14400, SR)
+    syn.close()
+    vd = np.zeros(1, dtype=s2.VOICE_DESC)
+    vd[0] = p.voice
+    vd["pitch_hz"] = s2.note_to_pitch(60); vd["active"] = 1; vd["release_offset"] = 9600
+    o, _ = oracle.bank_render(vd, oracle.bank_init_states(vd), SR, s2.FILTER_BIQUAD_HP, 14400, want_bus=False)
+    assert_parity(o[0], got, "high-pass patch")

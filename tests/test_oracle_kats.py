@@ -288,3 +288,61 @@ def test_bank_render_equals_per_voice_calls_and_carries_state():
     st_mt = oracle.bank_init_states(b)
     mt, _ = oracle.bank_render(b, st_mt, 48000, 0, 400, nthreads=3)
     assert mt.tobytes() == whole.tobytes()
+
+
+# ---- the rest of dsp_filters.rs: derived known answers -------------------------
+
+def _dsp_filter_f64(kind, sr, freq, dq, x):
+    """Independent binary64 restatement of dsp_filters.rs:12-230 (same formulas, numpy doubles)."""
+    th = 2.0 * np.pi * freq / sr
+    y = np.zeros_like(x, dtype=np.float64)
+    x1 = x2 = y1 = y2 = 0.0
+    if kind in ("lp2", "hp2", "bp2"):
+        if kind == "bp2":
+            tn = np.tan(th / (2.0 * dq))
+            beta = 0.5 * (1 - tn) / (1 + tn)
+            alpha = (0.5 - beta) / 2.0
+        else:
+            beta = 0.5 * (1 - dq / 2 * np.sin(th)) / (1 + dq / 2 * np.sin(th))
+        gamma = (0.5 + beta) * np.cos(th)
+        if kind == "lp2":
+            alpha = (0.5 + beta - gamma) / 4.0
+        if kind == "hp2":
+            alpha = (0.5 + beta + gamma) / 4.0
+        for i, v in enumerate(x):
+            s = {"lp2": v + 2 * x1 + x2, "hp2": v - 2 * x1 + x2, "bp2": v - x2}[kind]
+            out = 2.0 * (alpha * s + gamma * y1 - beta * y2)
+            x2, x1, y2, y1 = x1, v, y1, out
+            y[i] = out
+    else:
+        gamma = np.cos(th) / (1 + np.sin(th))
+        alpha = (1 + gamma) / 2 if kind == "hp1" else (1 - gamma) / 2
+        for i, v in enumerate(x):
+            out = alpha * ((v - x1) if kind == "hp1" else (v + x1)) + gamma * y1
+            x1, y1 = v, out
+            y[i] = out
+    return y
+
+
+@pytest.mark.parametrize("kind,freq,dq", [("lp2", 1000.0, 0.7), ("hp2", 1000.0, 0.7), ("hp2", 4000.0, 1.414),
+                                          ("bp2", 1500.0, 3.0), ("bp2", 3000.0, 0.8), ("lp1", 800.0, 0.0), ("hp1", 800.0, 0.0)])
+def test_dsp_filters_match_a_binary64_restatement(kind, freq, dq):
+    L = oracle.lib()
+    rng = np.random.default_rng(5)
+    x = np.concatenate([np.ones(256), rng.uniform(-1, 1, 768)]).astype(np.float32)
+    st = np.zeros(1, dtype=oracle.LAYER_STATE)
+    got = np.zeros(x.size, dtype=np.float32)
+    for i, v in enumerate(x):
+        if kind == "lp2":
+            got[i] = L.s2o_biquad_lp_process(oracle._p(st), 48000, freq, dq, float(v))
+        elif kind == "hp2":
+            got[i] = L.s2o_biquad_hp_process(oracle._p(st), 48000, freq, dq, float(v))
+        elif kind == "bp2":
+            got[i] = L.s2o_biquad_bp_process(oracle._p(st), 48000, freq, dq, float(v))
+        else:
+            got[i] = L.s2o_first_order_process(oracle._p(st), 48000, freq, 1 if kind == "hp1" else 0, float(v))
+    ref = _dsp_filter_f64(kind, 48000.0, freq, dq, x.astype(np.float64))
+    assert np.max(np.abs(got - ref)) < 2e-4
+    # the responses the names promise: DC passes a low-pass, is blocked by a high-pass and a band-pass
+    dc = got[200:256].mean()
+    assert abs(dc - (1.0 if kind in ("lp2", "lp1") else 0.0)) < 2e-3

@@ -8,9 +8,11 @@
              f32 render kept on the device (62.9 GB of the 180 GB)
 
 Prints one JSON line per config: voice-samples/s and the fraction of the measured HBM roofline at
-4 algorithmic bytes per voice-sample.  `PYTHONPATH=. python tools/measure_configs.py [2] [4] [5]`.
+4 algorithmic bytes per voice-sample.  `PYTHONPATH=. python tools/measure_configs.py [2] [2b] [4] [5]`; under
+`torchrun --nproc-per-node 8` every rank measures its own GPU (config 5: the rank is the sweep's GPU index).
 """
 import json
+import os
 import pathlib
 import sys
 
@@ -21,6 +23,9 @@ from synth2_b200 import bankgen
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 SR = 48000
+# under torchrun every rank measures its own GPU (config 5: rank = the sweep's GPU index; no collective)
+RANK = int(os.environ.get("RANK", "0"))
+DEV = int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def peak_gbs():
@@ -43,7 +48,7 @@ def timed(stream, bank, body):
 
 def report(name, voices, frames, seconds, **extra):
     vs = voices * frames / seconds
-    print(json.dumps({"config": name, "voices": voices, "frames_per_voice": frames, "seconds": seconds,
+    print(json.dumps({"rank": RANK, "config": name, "voices": voices, "frames_per_voice": frames, "seconds": seconds,
                       "voice_samples_per_s": vs, "hbm_GBs": vs * 4 / 1e9, "frac_of_measured_hbm": vs * 4 / 1e9 / peak_gbs(),
                       **extra}), flush=True)
 
@@ -52,7 +57,7 @@ def config2(stream):
     V, T, blocks = 1024, 4096, 256
     voices = bankgen.make_bank(V, 4 * blocks * T)
     for time_split in (False, True):
-        bank = s2.VoiceBank(voices, SR, s2.FILTER_ONE_POLE, device=0, stream=stream)
+        bank = s2.VoiceBank(voices, SR, s2.FILTER_ONE_POLE, device=DEV, stream=stream)
         if time_split:
             bank.set_time_split(True)
         ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
@@ -77,7 +82,7 @@ def config2_biquad(stream):
     V, T, blocks = 1024, 4096, 256
     voices = bankgen.make_bank(V, 4 * blocks * T, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     for time_split in (False, True):
-        bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=0, stream=stream)
+        bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=DEV, stream=stream)
         if time_split:
             bank.set_time_split(True)
         ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
@@ -93,7 +98,7 @@ def config2_biquad(stream):
 def config4(stream):
     V, T, blocks = 32768, 4096, 118            # 10 s
     voices = bankgen.make_bank(V, blocks * T, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
-    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=0, stream=stream)
+    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=DEV, stream=stream)
     bank.set_pipeline(4)
     ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(2)]
     master = torch.empty(blocks * T, device="cuda", dtype=torch.float32)
@@ -110,8 +115,8 @@ def config4(stream):
 
 def config5(stream):
     V, total, T = bankgen.SWEEP_VARIANTS, 480000, 4096
-    voices = bankgen.make_sweep_bank(0, total)
-    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=0, stream=stream)
+    voices = bankgen.make_sweep_bank(RANK, total)
+    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=DEV, stream=stream)
     bank.set_pipeline(4)
     out = torch.empty((V, total), device="cuda", dtype=torch.float32)          # 62.9 GB
     st = bank.get_state()
@@ -138,7 +143,7 @@ def config5(stream):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["2", "2b", "4", "5"]
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(DEV)
     stream = torch.cuda.current_stream()
     for w in which:
         {"2": config2, "2b": config2_biquad, "4": config4, "5": config5}[w](stream)
