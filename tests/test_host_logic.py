@@ -124,7 +124,7 @@ def test_argument_validation_happens_before_the_device():
     assert rc == _lib.S2_ERR_INVALID
     rc = s2.lib().s2_bank_create(0, 0, 0, 2, _lib.ptr(v), None, C.byref(h))
     assert rc == _lib.S2_ERR_INVALID
-    rc = s2.lib().s2_bank_create(0, 48000, 5, 2, _lib.ptr(v), None, C.byref(h))
+    rc = s2.lib().s2_bank_create(0, 48000, 6, 2, _lib.ptr(v), None, C.byref(h))      # kinds 0..5 exist
     assert rc == _lib.S2_ERR_INVALID
     assert b"filter_kind" in s2.lib().s2_last_error()
     assert s2.lib().s2_bank_render(None, 16, None, 0, None) == _lib.S2_ERR_INVALID
