@@ -656,12 +656,20 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
 // so the cutoff — and with it the filter coefficients — changes every frame (process.rs:148-152,
 // 363-371; the first 200 ms of every note of the default patch, synth.rs:141-150).  Everything else
 // keeps its fast form; envelopes are evaluated per frame with their full stage chain.
-template <int FILTER, int KIND, int TRACE, class ENV>
+// SHARED: every voice of the warp has the same cutoff trajectory (same cutoff, damping, modulation amount, mod
+// envelope and frame offset — a detune / pitch sweep of one patch, BASELINE config 5), so the 32 frames'
+// coefficients were computed once, one frame per lane, into `ctab` ([c0 | c1 | c2 | fl bits][32], see
+// modcut_coefficients): the same make_filt on the same inputs, hence the same bits, at 1/32 of the work.
+template <int FILTER, int KIND, int TRACE, bool SHARED, class ENV>
 __device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict__ amp, const ENV* __restrict__ mod,
                                              float lpf, float amt_lpf, float damp, float sr, FiltC& fc, uint32_t kind,
-                                             uint32_t rot, uint32_t n0, float* __restrict__ row, const float* sintab) {
-    const ENV A = *amp, M = *mod;
-    SegEnv sa = seg_env(A, n0), sm = seg_env(M, n0);
+                                             uint32_t rot, uint32_t n0, float* __restrict__ row, const float* sintab,
+                                             const float* __restrict__ ctab) {
+    const ENV A = *amp;
+    ENV M;
+    if (!SHARED) M = *mod;
+    SegEnv sa = seg_env(A, n0), sm = {0.0f, 0.0f, 0.0f, 0u};
+    if (!SHARED) sm = seg_env(M, n0);
     OscC o;
     o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
@@ -673,14 +681,20 @@ __device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict_
         float o4[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            float g, m;
+            float g;
             if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(A, xf); sa = seg_env(A, n + 1u); }
-            if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
-            // branch-free on purpose: 2^(m * 0) * f == f exactly, and re-deriving unchanged coefficients
-            // gives the same bits, so voices whose cutoff does not move lose nothing and the warp does not
-            // diverge around the binary64 code
-            const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
-            make_filt<FILTER>(fc, fl, damp, sr);
+            if (SHARED) {
+                const int fi = 4 * j + i;
+                fc.c0 = ctab[fi]; fc.c1 = ctab[32 + fi]; fc.c2 = ctab[64 + fi];
+            } else {
+                float m;
+                if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
+                // branch-free on purpose: 2^(m * 0) * f == f exactly, and re-deriving unchanged coefficients
+                // gives the same bits, so voices whose cutoff does not move lose nothing and the warp does not
+                // diverge around the binary64 code
+                const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
+                make_filt<FILTER>(fc, fl, damp, sr);
+            }
             const float ph0 = ph;
             const float osc = osc_step<KIND, false>(kind, o, ph, sintab);
             const float nz = noise_fast(rot, n);
@@ -692,8 +706,20 @@ __device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict_
         }
         *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
+    if (SHARED) fc.fl_bits = __float_as_uint(ctab[96 + kChunk - 1]);      // keep the memo key of the last frame
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+}
+
+// One frame per lane: the filter coefficients of frames n0 .. n0 + 31 of a cutoff trajectory shared by the warp.
+template <int FILTER, class ENV>
+__device__ __forceinline__ void modcut_coefficients(const ENV& M, float lpf, float amt_lpf, float damp, float sr,
+                                                    uint32_t n0, int lane, float* __restrict__ ctab) {
+    const float m = env_x16(M, __uint2float_rn(n0 + (uint32_t)lane));
+    const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
+    FiltC c;
+    make_filt<FILTER>(c, fl, damp, sr);
+    ctab[lane] = c.c0; ctab[32 + lane] = c.c1; ctab[64 + lane] = c.c2; ctab[96 + lane] = fl;
 }
 
 // General frame: the normative per-sample semantics, x16 or scalar-tail flavour.
@@ -759,10 +785,11 @@ struct Cold {
 };
 constexpr int kColdWords = (sizeof(Cold) / 4) | 1;
 constexpr int kRowPtrWords = 2;    // one 64-bit output-row base per tile row (0 = the row has no output)
+constexpr int kCoefWords = 128;    // shared moving-cutoff coefficients of one chunk: [c0 | c1 | c2 | fl][32]
 
 template <int NV>
 __host__ __device__ constexpr size_t warp_smem_floats() {
-    return 32 * NV * kTileStride + 32 * NV * kColdWords + 32 * NV * kRowPtrWords;
+    return 32 * NV * kTileStride + 32 * NV * kColdWords + 32 * NV * kRowPtrWords + kCoefWords;
 }
 
 }  // namespace s2

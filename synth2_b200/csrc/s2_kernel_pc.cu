@@ -276,10 +276,10 @@ __device__ __noinline__ ConsState pc_solo_modcut(ColdPc& C, ConsState st, int wk
     const float lpf = C.lpf, amt = C.amt_lpf, damp = C.damp;
     const uint32_t rot = C.rot, kind = C.kind, n = st.n;
     switch (wkind) {
-    case 0: chunk_modcut<FILTER, 0, TRACE_NONE>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab); break;
-    case 1: chunk_modcut<FILTER, 1, TRACE_NONE>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab); break;
-    case 2: chunk_modcut<FILTER, 2, TRACE_NONE>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab); break;
-    default: chunk_modcut<FILTER, -1, TRACE_NONE>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab); break;
+    case 0: chunk_modcut<FILTER, 0, TRACE_NONE, false>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab, nullptr); break;
+    case 1: chunk_modcut<FILTER, 1, TRACE_NONE, false>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab, nullptr); break;
+    case 2: chunk_modcut<FILTER, 2, TRACE_NONE, false>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab, nullptr); break;
+    default: chunk_modcut<FILTER, -1, TRACE_NONE, false>(F, &C.amp, &C.mod, lpf, amt, damp, sr, fc, kind, rot, n, row, sintab, nullptr); break;
     }
     if (active) C.fc = fc;
     st.ph = F.ph; st.fs.x1 = F.x1; st.fs.x2 = F.x2; st.fs.y1 = F.y1; st.fs.y2 = F.y2;

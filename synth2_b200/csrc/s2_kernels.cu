@@ -150,6 +150,27 @@ render_kernel(const RenderArgs a) {
     // offsets advance by whole 32-frame chunks while on the fast path, so this holds for the launch
     const bool aligned8 = __all_sync(0xffffffffu, lane_al8);
 
+    // Do the active voices of the warp share one cutoff trajectory (cutoff, damping, modulation amount, mod
+    // envelope, frame offset)?  Then a moving-cutoff chunk computes its 32 frames' coefficients once, one frame
+    // per lane (chunk_modcut<..., SHARED>).  Offsets advance together, so this holds for the launch.
+    bool filt_uniform = false;
+    if (NV == 1) {
+        const unsigned am = __ballot_sync(0xffffffffu, active[0]);
+        const int uni_leader = am ? __ffs(am) - 1 : 0;
+        const Cold& C = cold(0);
+        const EnvP& M = C.L.mod;
+        const float key[10] = {C.L.lpf, C.L.damp, C.L.amt_lpf, M.A, M.AD, M.S, M.Rs, M.E, M.sD, M.sR};
+        // (every lane must execute every shuffle: no short-circuit between them)
+        const uint32_t n_lead = __shfl_sync(0xffffffffu, n[0], uni_leader);
+        const float sa_lead = __shfl_sync(0xffffffffu, M.sA, uni_leader);
+        bool same = n_lead == n[0];
+        same &= __float_as_uint(sa_lead) == __float_as_uint(M.sA);
+#pragma unroll
+        for (int k = 0; k < 10; k++)
+            same &= __float_as_uint(__shfl_sync(0xffffffffu, key[k], uni_leader)) == __float_as_uint(key[k]);
+        filt_uniform = am != 0u && __all_sync(0xffffffffu, same || !active[0]);
+    }
+
     const uint32_t frames = a.frames;
     const uint32_t f16 = frames & ~15u;            // x16 region (process.rs:26-37), then the scalar tail
     const size_t stride = a.row_stride;
@@ -308,11 +329,28 @@ render_kernel(const RenderArgs a) {
                 FiltC fc = C.fc;
                 float* row = tile + lane * kTileStride;
                 const float lpf = C.L.lpf, amt = C.L.amt_lpf, damp = C.L.damp;
+                if (filt_uniform) {
+                    // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once
+                    float* ctab = cold_base + kRows * kColdWords + kRows * kRowPtrWords;
+                    const int uni_leader = __ffs(__ballot_sync(0xffffffffu, active[0])) - 1;      // filt_uniform => some lane is active
+                    const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + uni_leader * kColdWords);
+                    const uint32_t n_lead = __shfl_sync(0xffffffffu, n[0], uni_leader);   // inactive lanes hold other offsets
+                    modcut_coefficients<FILTER>(CL.L.mod, CL.L.lpf, CL.L.amt_lpf, CL.L.damp, sr, n_lead, lane, ctab);
+                    __syncwarp();
+                    switch (wkind) {
+                    case 0: chunk_modcut<FILTER, 0, TRACE, true>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, ctab); break;
+                    case 1: chunk_modcut<FILTER, 1, TRACE, true>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, ctab); break;
+                    case 2: chunk_modcut<FILTER, 2, TRACE, true>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, ctab); break;
+                    default: chunk_modcut<FILTER, -1, TRACE, true>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, ctab); break;
+                    }
+                    __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
+                } else {
                 switch (wkind) {
-                case 0: chunk_modcut<FILTER, 0, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
-                case 1: chunk_modcut<FILTER, 1, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
-                case 2: chunk_modcut<FILTER, 2, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
-                default: chunk_modcut<FILTER, -1, TRACE>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab); break;
+                case 0: chunk_modcut<FILTER, 0, TRACE, false>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, nullptr); break;
+                case 1: chunk_modcut<FILTER, 1, TRACE, false>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, nullptr); break;
+                case 2: chunk_modcut<FILTER, 2, TRACE, false>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, nullptr); break;
+                default: chunk_modcut<FILTER, -1, TRACE, false>(F, &C.L.amp, &C.L.mod, lpf, amt, damp, sr, fc, kind[0], rot[0], n[0], row, sintab, nullptr); break;
+                }
                 }
                 if (active[0]) C.fc = fc;
                 n[0] += kChunk;

@@ -593,7 +593,13 @@ def test_sweep_variants_config5():
     got, _, st = gpu_bank_render(sub, 1, blocks, want_bus=False)
     assert_parity(ref, got, "sweep sample")
     assert_state_parity(st, rst, 1)
-    # full width, first block: the sample's rows come out bit-identical inside the 32,768-variant bank
+    # full width, first block: the sample's rows come out bit-identical inside the 32,768-variant bank.  There
+    # every warp is 32 detunes of one (cutoff, damping) pair, so the moving-cutoff chunks compute their
+    # coefficients once per warp, one frame per lane (chunk_modcut<SHARED>); the 64-variant sample above took the
+    # per-voice form.  Silent voices parked at another frame offset must not disturb their warp.
+    idle = np.setdiff1d(np.arange(7, 32768, 32), pick)
+    v["active"][idle] = 0
+    v["frame_offset"][idle] = 777
     out = torch.empty((32768, T), device="cuda", dtype=torch.float32)
     with s2.VoiceBank(v, SR, 1) as bank:
         bank.set_pipeline(4)
@@ -602,6 +608,7 @@ def test_sweep_variants_config5():
     assert bool(torch.isfinite(out).all())
     rows = out[torch.as_tensor(pick, device="cuda")].cpu().numpy()
     assert rows.tobytes() == got[:, :T].tobytes()
+    assert bool((out[torch.as_tensor(idle, device="cuda")] == 0).all())
     # release at 75 % of a short render: the tail decays to silence for every variant
     short = bankgen.make_sweep_bank(1, 16384, first_variant=0, n_variants=1024)
     o, _, _ = gpu_bank_render(short, 1, [16384, 4096 + 2048], want_bus=False)
