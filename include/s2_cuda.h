@@ -158,8 +158,9 @@ int s2_bank_join(s2_bank* bank, void* stream);
 /*
  * Time-split mode for narrow banks (BASELINE config 2: 1,024 voices, 4,096-frame buffers).
  * With one voice per lane a bank of a thousand voices leaves most of the GPU idle; enable = 1 lets blocks
- * whose voices all hold one period and one cutoff (no pitch modulation, mod envelope at rest or unused by
- * the cutoff) and whose length is a multiple of 1,024 frames render as 32 time segments per voice: the
+ * whose voices all hold one period (no pitch modulation) and whose length is a multiple of 1,024 frames
+ * render as 32 time segments per voice (with per-frame filter coefficients where a cutoff follows a ramping
+ * mod envelope, constant ones otherwise): the
  * oscillator phase is stepped alone and exactly (try3/oscillators.rs:377-381, bit-exact as always), the
  * filter state — one-pole `last` (try3/filters.rs:15-34) or the (y1, y2) of the second-order low-pass
  * (try3/dsp_filters.rs:116-128) — enters each segment through a prefix scan of the segments' affine maps.

@@ -288,22 +288,24 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
 // units.rs:44-53 in host f32 arithmetic (IEEE, no contraction: same bits as the device's make_env)
 float host_ms_as_samples(float ms, float sr) { return sr * (ms / 1000.0f); }
 
-// May this block go through the time-split kernels?  Every active voice must keep one period and one
-// cutoff for the whole block: no pitch modulation, and the mod envelope either unused by the cutoff or
-// resting (sustain / end) until the block ends.  Conservative: anything unsure renders the general way.
-bool ts_block_eligible(const s2_bank* b, size_t frames, const float* d_voice_out, const float* d_bus_out) {
-    if (!b->ts_enabled || !d_voice_out || d_bus_out) return false;
-    if (frames < 1024 || (frames & 1023u) != 0 || frames > (1u << 24)) return false;   // 32 segments of whole chunks
+// May this block go through the time-split kernels?  Every active voice must keep one period for the whole
+// block (no pitch modulation).  Returns 0 = no, 1 = yes and every cutoff rests too (mod envelope unused by the
+// cutoff, or in sustain / end until the block ends), 2 = yes but some cutoff follows a ramping mod envelope
+// (per-frame coefficients).  Conservative: anything unsure renders the general way.
+int ts_block_class(const s2_bank* b, size_t frames, const float* d_voice_out, const float* d_bus_out) {
+    if (!b->ts_enabled || !d_voice_out || d_bus_out) return 0;
+    if (frames < 1024 || (frames & 1023u) != 0 || frames > (1u << 24)) return 0;   // 32 segments of whole chunks
     const float sr = (float)b->sample_rate;
+    int cls = 1;
     for (size_t i = 0; i < b->n_voices; i++) {
         if (!b->book[i].active) continue;
         const s2_voice_desc& d = b->descs[i];
-        if (d.mod_env_to_osc_freq != 0.0f) return false;
+        if (d.mod_env_to_osc_freq != 0.0f) return 0;
         const uint64_t n0 = current_offset(b, i);
-        if (n0 + frames > (1ull << 24)) return false;
+        if (n0 + frames > (1ull << 24)) return 0;
         const float P = sr / d.pitch_hz;
         const float step = 1.0f / P;
-        if (!(step < 1.0f && P > 1.0f)) return false;
+        if (!(step < 1.0f && P > 1.0f)) return 0;
         if (d.mod_env_to_lpf_freq != 0.0f) {
             const float A = host_ms_as_samples(d.mod_attack_ms, sr), D = host_ms_as_samples(d.mod_decay_ms, sr);
             const float R = host_ms_as_samples(d.mod_release_ms, sr);
@@ -313,13 +315,13 @@ bool ts_block_eligible(const s2_bank* b, size_t frames, const float* d_voice_out
             const float x0 = (float)(uint32_t)n0, x1 = (float)(uint32_t)(n0 + frames - 1);
             const bool rest_sustain = x0 >= A && x0 >= AD && x1 < Rs;     // stage 2 from first to last frame
             const bool rest_end = x0 >= A && x0 >= AD && x0 >= Rs && x0 >= E;
-            if (!(rest_sustain || rest_end)) return false;
+            if (!(rest_sustain || rest_end)) cls = 2;
         }
     }
-    return true;
+    return cls;
 }
 
-int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride) {
+int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, bool moving) {
     const int p = (int)(b->ts_step % (uint64_t)kTsBufs);
     s2::RenderArgs a;
     a.params = b->d_params;
@@ -344,7 +346,7 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     CUDA_TRY(s2::launch_ts_phase(a, b->d_seg_phase[p], b->ts));
     CUDA_TRY(cudaEventRecord(b->ev_k1[p], b->ts));
     CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_k1[p], 0));
-    CUDA_TRY(s2::launch_ts_render(a, b->filter_kind, b->d_seg_phase[p], b->stream));
+    CUDA_TRY(s2::launch_ts_render(a, b->filter_kind, moving, b->d_seg_phase[p], b->stream));
     CUDA_TRY(cudaEventRecord(b->ev_k2[p], b->stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);
     b->ts_step++;
@@ -366,8 +368,10 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     if (b->max_offset + frames > 0xFFFFFFFFull)
         return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
     CUDA_TRY(cudaSetDevice(b->device));
-    if (trace == s2::TRACE_NONE && ts_block_eligible(b, frames, d_voice_out, d_bus_out))
-        return bank_render_time_split(b, frames, d_voice_out, row_stride);
+    if (trace == s2::TRACE_NONE) {
+        const int cls = ts_block_class(b, frames, d_voice_out, d_bus_out);
+        if (cls) return bank_render_time_split(b, frames, d_voice_out, row_stride, cls == 2);
+    }
     b->ts_main_dirty = true;      // the general kernels below move the carried phase on the bank's stream
     if (b->n_sub > 1 && trace == s2::TRACE_NONE) return bank_render_pipelined(b, frames, d_voice_out, row_stride, d_bus_out);
     if (b->n_sub > 1) { int rc = bank_drain(b); if (rc) return rc; }

@@ -64,7 +64,9 @@ cudaError_t launch_render_pc(const RenderArgs& a, uint32_t filter_kind, cudaStre
 // the render consumes it.
 // frames must be a multiple of 1024.
 cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t stream);
-cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, const float* seg_phase, cudaStream_t stream);
+// moving: some voice's cutoff follows a ramping mod envelope in this block (per-frame coefficients)
+cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, bool moving, const float* seg_phase,
+                             cudaStream_t stream);
 // two kernels; seg_scratch holds bus_segments(n_warps) * frames floats
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
                               float* bus, cudaStream_t stream);

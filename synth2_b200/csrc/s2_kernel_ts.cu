@@ -25,8 +25,9 @@
 //
 // Parity: phase bit-exact (same recurrence, same order); output within the north-star tolerance (the start
 // state of segments 1..31 carries the scan's reassociation error, ~1 ulp of the state, and decays as k^n).
-// Used only when every voice of the block has a constant period and cutoff (host check in s2_capi.cu);
-// anything else renders through the wide-bank kernel.
+// Used only when every voice of the block has a constant period (host check in s2_capi.cu: no pitch modulation);
+// anything else renders through the wide-bank kernel.  Where a cutoff follows a ramping mod envelope the sweeps
+// evaluate the coefficients per frame (ts_moving_sweep) and the segment map is the product of the per-frame maps.
 #include "s2_device.cuh"
 
 namespace s2 {
@@ -91,8 +92,63 @@ __device__ __forceinline__ M22 shfl_up(const M22& m, int off) {
             __shfl_up_sync(0xffffffffu, m.c, off), __shfl_up_sync(0xffffffffu, m.d, off)};
 }
 
+// One sweep over a lane's segment with a MOVING cutoff (the mod envelope is in a ramp: the first 200 ms of every
+// note of the default patch).  Per frame, exactly the moving-cutoff chunk of the wide-bank kernel (chunk_modcut:
+// envelopes by stage line, 2^(m*amt), make_filt, oscillator, noise, filter step); the first sweep also
+// accumulates the product of the per-frame state maps — k_n for the one-pole, M_n = [[2g_n, -2b_n], [1, 0]] for
+// the biquad — which is the segment's map for the scan.  WRITE: second sweep, output through the tile.
+template <int FILTER, bool WRITE>
+__device__ __forceinline__ void ts_moving_sweep(const EnvP& A, const EnvP& M, float lpf, float amt_lpf, float damp,
+                                                float sr, const OscC& oc, uint32_t kind, uint32_t rot, float gain,
+                                                float namt, uint32_t nl, uint32_t L, float& ph, FiltS& fs, float& kprod,
+                                                M22& mprod, float* tile, int lane, float* __restrict__ gout,
+                                                const float* sintab) {
+    const int q = lane >> 3, c4 = (lane & 7) * 4;
+    float* row = tile + lane * kTileStride;
+    SegEnv sa = seg_env(A, nl), sm = seg_env(M, nl);
+    uint32_t n = nl;
+    float xf = __uint2float_rn(nl);
+    FiltC fc;
+    for (uint32_t c = 0; c < L; c += kChunk) {
+#pragma unroll 2
+        for (int i = 0; i < kChunk; i++) {
+            float m;
+            if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
+            const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
+            make_filt<FILTER>(fc, fl, damp, sr);
+            const float osc = osc_step<-1, false>(kind, oc, ph, sintab);
+            const float u = __fadd_rn(__fadd_rn(osc, gain), __fadd_rn(noise_fast(rot, n), namt));
+            const float y = filt_step<FILTER>(u, fc, fs);
+            if (!WRITE) {
+                if (FILTER == 0) kprod = __fmul_rn(kprod, fc.c0);
+                else {                                        // M_n * mprod
+                    const double g2 = (double)fc.c2, b2 = (double)fc.c1;
+                    const M22 t = {fma(g2, mprod.a, -b2 * mprod.c), fma(g2, mprod.b, -b2 * mprod.d), mprod.a, mprod.b};
+                    mprod = t;
+                }
+            } else {
+                float g;
+                if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(A, xf); sa = seg_env(A, n + 1u); }
+                row[i] = __fmul_rn(y, g);
+            }
+            n += 1u;
+            xf = __fadd_rn(xf, 1.0f);
+        }
+        if (WRITE) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = 4 * i + q;                      // tile row = segment r
+                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+                __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // K2: one warp per voice slot; lane = time segment.
-template <int FILTER>
+template <int FILTER, bool MOVING>
 __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const float* __restrict__ seg_phase) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;                                      // [32 segments][kTileStride]
@@ -162,15 +218,25 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     }
 
     // ---- sweep 1: zero-state response of the segment (gain and output are irrelevant)
-    F.ph = ph0;
-    F.x1 = x1_in; F.x2 = x2_in; F.y1 = 0.0f; F.y2 = 0.0f;
-    for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, kind, rot, nl + c, row, sintab);
+    float kprod = 1.0f;
+    M22 mprod = {1.0, 0.0, 0.0, 1.0};
+    if (MOVING) {
+        float ph = ph0;
+        FiltS fs = {x1_in, x2_in, 0.0f, 0.0f};
+        ts_moving_sweep<FILTER, false>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, oc, kind, rot, F.gain, F.namt,
+                                       nl, L, ph, fs, kprod, mprod, tile, lane, gout, sintab);
+        F.y1 = fs.y1; F.y2 = fs.y2;
+    } else {
+        F.ph = ph0;
+        F.x1 = x1_in; F.x2 = x2_in; F.y1 = 0.0f; F.y2 = 0.0f;
+        for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, kind, rot, nl + c, row, sintab);
+    }
 
     // ---- the segment maps compose left to right: inclusive Hillis-Steele scan over the lanes
     float y1_in, y2_in = 0.0f;
     if (FILTER == 0) {
         const float last = S[S_LAST * vp];
-        float Kc = (float)exp((double)L * log((double)fc.c0));   // k^L (one value per voice)
+        float Kc = MOVING ? kprod : (float)exp((double)L * log((double)fc.c0));   // k^L (one value per voice)
         float Yc = F.y1;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -186,8 +252,8 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
         if (lane == 0) y1_in = last;
     } else {
         // one frame: (y1, y2)' = M (y1, y2) + (2a*s, 0),  M = [[2g, -2b], [1, 0]]  (filt_step<1>)
-        M22 Mc = {1.0, 0.0, 0.0, 1.0};
-        {
+        M22 Mc = mprod;
+        if (!MOVING) {
             M22 base = {(double)fc.c2, -(double)fc.c1, 1.0, 0.0};
             for (uint32_t e = L; e; e >>= 1) {                // M^L by squaring
                 if (e & 1u) Mc = mul(base, Mc);
@@ -215,18 +281,26 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     }
 
     // ---- sweep 2: the reference recurrence from the true start state, written out
-    F.ph = ph0;
-    F.x1 = x1_in; F.x2 = x2_in; F.y1 = y1_in; F.y2 = y2_in;
-    for (uint32_t c = 0; c < L; c += kChunk) {
-        ts_chunk_kind<FILTER, false>(F, &A, kind, rot, nl + c, row, sintab);
-        __syncwarp();
+    if (MOVING) {
+        float ph = ph0;
+        FiltS fs = {x1_in, x2_in, y1_in, y2_in};
+        ts_moving_sweep<FILTER, true>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, oc, kind, rot, F.gain, F.namt,
+                                      nl, L, ph, fs, kprod, mprod, tile, lane, gout, sintab);
+        F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+    } else {
+        F.ph = ph0;
+        F.x1 = x1_in; F.x2 = x2_in; F.y1 = y1_in; F.y2 = y2_in;
+        for (uint32_t c = 0; c < L; c += kChunk) {
+            ts_chunk_kind<FILTER, false>(F, &A, kind, rot, nl + c, row, sintab);
+            __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r = 4 * i + q;                          // tile row = segment r
-            const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
-            __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
+            for (int i = 0; i < 8; i++) {
+                const int r = 4 * i + q;                      // tile row = segment r
+                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+                __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     if (lane == 31) {
         if (FILTER == 0) S[S_LAST * vp] = F.y1;
@@ -243,11 +317,17 @@ cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, const float* seg_phase, cudaStream_t stream) {
+cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, bool moving, const float* seg_phase,
+                             cudaStream_t stream) {
     if (a.n_voices == 0) return cudaSuccess;
     const size_t smem = (32 * kTileStride + 1024) * sizeof(float);
-    if (filter_kind == 0) ts_render_kernel<0><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
-    else ts_render_kernel<1><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    if (filter_kind == 0) {
+        if (moving) ts_render_kernel<0, true><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+        else ts_render_kernel<0, false><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    } else {
+        if (moving) ts_render_kernel<1, true><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+        else ts_render_kernel<1, false><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
+    }
     return cudaGetLastError();
 }
 

@@ -636,14 +636,14 @@ def _render_blocks(voices, filter_kind, blocks, time_split, kinds_stride=None):
 
 def test_time_split_config2_against_oracle():
     """BASELINE config 2 through the time-split kernels: 1,024 saw/square voices + one-pole low-pass,
-    4,096-frame buffers, carried state.  The first blocks (200 ms mod-envelope decay on half the voices)
-    do not qualify and take the default path; the rest render as 32 segments per voice.  Phase bit-exact,
-    output within the north-star tolerance, against the oracle and against the default path."""
+    4,096-frame buffers, carried state.  Every block renders as 32 segments per voice: the first three
+    (200 ms mod-envelope decay on half the voices) with per-frame filter coefficients, the rest with constant
+    ones.  Phase bit-exact, output within the north-star tolerance, against the oracle and the default path."""
     V, T, N = 1024, 4096, 6
     v = bank_for(0, V, 400000)
     ref, _, rst = oracle_bank_render(v, 0, [T] * N)
     got, st, n_ts = _render_blocks(v, 0, [T] * N, True)
-    assert n_ts == N - 3                      # blocks 0-2 hold the 9,600-frame mod decay
+    assert n_ts == N
     assert_parity(ref, got, "config 2 time-split vs oracle")
     assert_state_parity(st, rst, 0)
     plain, st0, n0 = _render_blocks(v, 0, [T] * N, False)
@@ -674,8 +674,8 @@ def test_time_split_envelopes_kinds_and_fallbacks():
 
 
 def test_time_split_follows_note_offs_and_mod_release():
-    """Voices whose cutoff follows the mod envelope qualify only while that envelope rests: a note-off that
-    starts a mod release inside a block sends that block to the default path, later blocks qualify again."""
+    """Blocks in which a cutoff follows a ramping mod envelope (decay after the note-on, release after the
+    note-off, stage changes mid-segment) take the per-frame-coefficient form of the time-split kernels."""
     V, T = 64, 2048
     v = bank_for(0, V, 10 * T)                # release at 15,360 = block 7.5
     v["mod_release_ms"] = 20.0
@@ -683,7 +683,7 @@ def test_time_split_follows_note_offs_and_mod_release():
     ref, _, rst = oracle_bank_render(v, 0, [T] * 10)
     got, st, n_ts = _render_blocks(v, 0, [T] * 10, True)
     # blocks 0-4 hold the 9,600-frame decay, block 7 the release start (and its 960-frame ramp)
-    assert n_ts == 10 - 5 - 1
+    assert n_ts == 10
     assert_parity(ref, got, "time-split mod release")
     assert_state_parity(st, rst, 0)
 
@@ -699,7 +699,7 @@ def test_time_split_biquad_2x2_scan():
     v["active"][5::17] = 0
     ref, _, rst = oracle_bank_render(v, 1, [T] * N)
     got, st, n_ts = _render_blocks(v, 1, [T] * N, True)
-    assert n_ts == N - 3                      # blocks 0-2 hold the mod decay of the voices whose cutoff follows it
+    assert n_ts == N                          # blocks 0-2 (mod decay) with per-frame 2x2 maps
     assert_parity(ref, got, "biquad time-split vs oracle")
     assert_state_parity(st, rst, 1)
     plain, st0, _ = _render_blocks(v, 1, [T] * N, False)
