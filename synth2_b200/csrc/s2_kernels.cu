@@ -60,7 +60,6 @@ render_kernel(const RenderArgs a) {
 
     const uint32_t vbase = a.slot_begin + (blockIdx.x * kWarpsPerBlock + warp) * kRows;
     if (vbase >= a.slot_end) return;
-    const uint32_t gwarp = vbase / kRows;          // index of this voice group in the whole bank
     const uint32_t vp = a.vpad;
     const float sr = a.sample_rate;
     auto cold = [&](int e) -> Cold& { return *reinterpret_cast<Cold*>(cold_base + (e * 32 + lane) * kColdWords); };
@@ -191,7 +190,6 @@ render_kernel(const RenderArgs a) {
     }
     __syncwarp();
     const bool all_rows = __all_sync(0xffffffffu, lane_rows_ok);   // every tile row has an output row
-    float* __restrict__ gbus = a.bus_partials ? a.bus_partials + (size_t)gwarp * frames : nullptr;
 
     // fast_left: frames for which every voice of the warp stays on the fast path (warp-uniform), with
     // the loop variant (gconst) chosen when it was computed; 0 = classify before the next chunk.
@@ -389,6 +387,11 @@ render_kernel(const RenderArgs a) {
         }
         __syncwarp();
         // (16-byte stores into this warp's partial row: needs frames % 4 == 0 and an aligned base)
+        // this warp's partial row, from launch parameters and the block index only (uniform registers: a pointer
+        // kept live across the chunk loop is spilled under the register cap and reloaded from local memory)
+        float* __restrict__ gbus = a.bus_partials
+            ? a.bus_partials + (size_t)(a.slot_begin / (uint32_t)kRows + blockIdx.x * (uint32_t)kWarpsPerBlock + (uint32_t)warp) * a.frames
+            : nullptr;
         const bool wide_bus = gbus != nullptr && a.n_voices > 32u && cnt == kChunk && (frames & 3u) == 0u &&
                               (reinterpret_cast<uintptr_t>(gbus) & 15u) == 0u;
         float2 b01 = make_float2(0.0f, 0.0f), b23 = make_float2(0.0f, 0.0f);
