@@ -956,3 +956,23 @@ def test_patch_selects_the_remaining_filters():
     vd["pitch_hz"] = s2.note_to_pitch(60); vd["active"] = 1; vd["release_offset"] = 9600
     o, _ = oracle.bank_render(vd, oracle.bank_init_states(vd), SR, s2.FILTER_BIQUAD_HP, 14400, want_bus=False)
     assert_parity(o[0], got, "high-pass patch")
+
+
+def test_compiled_example_renders_like_the_python_mirror(tmp_path):
+    """examples/render_patch.cpp drives the C ABI from C++ (no Python in the process)."""
+    import subprocess
+    from test_host_logic import build_example
+    exe = build_example(tmp_path)
+    text = ("synth s { osc { kind triangle } lpf { freq 600 } } "
+            "score { on 0 60; on 2400 64; off 9600 60; off 12000 64 }")
+    (tmp_path / "p.synth2").write_text(text)
+    res = subprocess.run([str(exe), str(tmp_path / "p.synth2"), "0.5", "48000", str(tmp_path / "o.f32")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = np.fromfile(tmp_path / "o.f32", dtype="<f4")
+    p = s2patch.parse(text, SR)
+    syn = s2.Synth()
+    syn.set_patch(p)
+    want = syn.render_score(p.events, 24000, SR)
+    syn.close()
+    assert got.tobytes() == want.tobytes()

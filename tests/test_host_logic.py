@@ -4,6 +4,7 @@ match the oracle, and the library refuses to compute without a GPU (no CPU fallb
 import ctypes as C
 import pathlib
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -349,3 +350,29 @@ def test_wav_writer_roundtrip(tmp_path):
     i = raw.index(b"data")
     assert int.from_bytes(raw[i + 4:i + 8], "little") == 4000
     assert np.frombuffer(raw[i + 8:], dtype="<f4").tobytes() == x.tobytes()
+
+
+# ---- the C ABI from compiled code (examples/render_patch.cpp) ---------------------------------
+
+def build_example(tmp_path):
+    exe = tmp_path / "render_patch"
+    cmd = ["g++", "-std=c++17", "-O1", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "render_patch.cpp"),
+           f"-L{ROOT / 'synth2_b200'}", "-ls2cuda", f"-Wl,-rpath,{ROOT / 'synth2_b200'}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_compiled_example_links_and_fails_loudly_without_a_gpu(tmp_path):
+    exe = build_example(tmp_path)
+    (tmp_path / "p.synth2").write_text(EXAMPLE_SYNTH2)
+    res = subprocess.run([str(exe), str(tmp_path / "p.synth2"), "0.01", "48000", str(tmp_path / "o.f32")],
+                         capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert res.returncode == 0, res.stderr
+    else:
+        assert res.returncode == 1 and "no CUDA device" in res.stderr       # no CPU path, said plainly
+    bad = subprocess.run([str(exe), str(tmp_path / "missing.synth2"), "1", "48000", str(tmp_path / "o.f32")],
+                         capture_output=True, text=True)
+    assert bad.returncode == 2
