@@ -54,6 +54,36 @@ def load(path, sample_rate: int = 48000) -> Patch:
         return parse(f.read(), sample_rate)
 
 
+_OSC_NAMES = {0: "square", 1: "saw", 2: "triangle", 3: "sine"}
+_FILTER_NAMES = {0: "one_pole", 1: "biquad", 2: "biquad_hp", 3: "biquad_bp", 4: "first_order", 5: "first_order_hp"}
+
+
+def dumps(p: Patch) -> str:
+    """The patch (and its score, in frames) as `.synth2` text that `parse` reads back to the same records."""
+    v = p.voice
+
+    def num(x):
+        return repr(float(np.float32(x)))          # shortest text that reads back to the same binary32
+
+    lines = [f"synth {p.name or 'patch'} {{",
+             f"    osc {{ kind {_OSC_NAMES[int(v['osc_kind'])]}; gain {num(v['osc_gain'])} }}",
+             f"    noise {num(v['noise_amt'])}",
+             f"    lpf {{ freq {num(v['lpf_freq_hz'])}; kind {_FILTER_NAMES[p.filter_kind]}; damping {num(v['damping'])} }}"]
+    for env in ("amp", "mod"):
+        lines.append(f"    {env}_env {{ attack {num(v[env + '_attack_ms'])}; decay {num(v[env + '_decay_ms'])}; "
+                     f"sustain {num(v[env + '_sustain'])}; release {num(v[env + '_release_ms'])} }}")
+    lines.append(f"    modulations {{ mod_env_to_osc_freq {num(v['mod_env_to_osc_freq'])}; "
+                 f"mod_env_to_lpf_freq {num(v['mod_env_to_lpf_freq'])} }}")
+    lines.append("}")
+    if p.events.size:
+        lines.append("score {")
+        for e in p.events:
+            lines.append(f"    on {int(e['frame'])} {int(e['note'])} {num(e['velocity'])}" if e["on"]
+                         else f"    off {int(e['frame'])} {int(e['note'])}")
+        lines.append("}")
+    return "\n".join(lines) + "\n"
+
+
 def make_events(items) -> np.ndarray:
     """[(frame, "on" | "off", note[, velocity]), ...] -> NOTE_EVENT records (kept in the given order)."""
     ev = np.zeros(len(items), dtype=NOTE_EVENT)

@@ -334,6 +334,21 @@ def test_patch_errors_name_the_line_and_field(text, needle):
     assert needle in str(e.value) and "patch line" in str(e.value)
 
 
+def test_patch_text_round_trip():
+    src = """synth lead { osc { kind sine; gain 0.3 } noise 0.0625
+        lpf { freq 1234.5; kind biquad_bp; damping 3.25 }
+        amp_env { attack 0.1; decay 33.3; sustain 0.7; release 250 }
+        mod_env { attack 2; decay 60; sustain 0.1; release 9 }
+        modulations { mod_env_to_osc_freq 0.25; mod_env_to_lpf_freq -2.5 } }
+        score { on 0 60 0.8; on 480 64; off 4800 60; off 9600 64 }"""
+    p = s2patch.parse(src)
+    q = s2patch.parse(s2patch.dumps(p))
+    assert q.record.tobytes() == p.record.tobytes()
+    assert q.events.tobytes() == p.events.tobytes()
+    d = s2patch.parse(s2patch.dumps(s2patch.default_patch()))
+    assert d.voice.tobytes() == s2.default_voice(1)[0].tobytes() and d.name == "patch"
+
+
 def test_patch_struct_layouts():
     assert s2.PATCH.itemsize == 144 and s2.PATCH.fields["filter_kind"][1] == 80 and s2.PATCH.fields["name"][1] == 84
     assert s2.NOTE_EVENT.itemsize == 16 and s2.NOTE_EVENT.fields["velocity"][1] == 12
