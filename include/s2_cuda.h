@@ -166,7 +166,8 @@ int s2_bank_join(s2_bank* bank, void* stream);
  * (try3/dsp_filters.rs:116-128) — enters each segment through a prefix scan of the segments' affine maps.
  * Output differs from the one-lane-per-voice render only by that scan's reassociation (north star
  * tolerance), so, unlike the default path, a block is not bit-identical to the same frames rendered as two
- * half blocks.  Blocks that do not qualify (and every bus / trace request) take the default path;
+ * half blocks.  A mix, when requested, is the sum of the rendered rows in voice order (so the rows must be
+ * requested too).  Blocks that do not qualify (and every trace request) take the default path;
  * s2_bank_time_split_blocks counts the blocks that did.  Banks of at most 16,384 voices only; exclusive
  * with s2_bank_set_pipeline(n_sub > 1); filter kinds ONE_POLE and BIQUAD_LP.
  */

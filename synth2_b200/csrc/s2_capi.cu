@@ -273,7 +273,7 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
         if (n_warps == 1) {
             CUDA_TRY(cudaMemcpyAsync(d_bus_out, partials, frames * sizeof(float), cudaMemcpyDeviceToDevice, b->mix));
         } else {
-            CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, partials + (size_t)n_warps * frames,
+            CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
                                            d_bus_out, b->mix));
             g_launches.fetch_add(2, std::memory_order_relaxed);
         }
@@ -293,7 +293,8 @@ float host_ms_as_samples(float ms, float sr) { return sr * (ms / 1000.0f); }
 // cutoff, or in sustain / end until the block ends), 2 = yes but some cutoff follows a ramping mod envelope
 // (per-frame coefficients).  Conservative: anything unsure renders the general way.
 int ts_block_class(const s2_bank* b, size_t frames, const float* d_voice_out, const float* d_bus_out) {
-    if (!b->ts_enabled || !d_voice_out || d_bus_out) return 0;
+    if (!b->ts_enabled || !d_voice_out) return 0;                               // the mix is summed from the rows
+    (void)d_bus_out;
     if (frames < 1024 || (frames & 1023u) != 0 || frames > (1u << 24)) return 0;   // 32 segments of whole chunks
     const float sr = (float)b->sample_rate;
     int cls = 1;
@@ -321,7 +322,8 @@ int ts_block_class(const s2_bank* b, size_t frames, const float* d_voice_out, co
     return cls;
 }
 
-int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, bool moving) {
+int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out,
+                           bool moving) {
     const int p = (int)(b->ts_step % (uint64_t)kTsBufs);
     s2::RenderArgs a;
     a.params = b->d_params;
@@ -349,6 +351,24 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     CUDA_TRY(s2::launch_ts_render(a, b->filter_kind, moving, b->d_seg_phase[p], b->stream));
     CUDA_TRY(cudaEventRecord(b->ev_k2[p], b->stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (d_bus_out) {
+        // one warp rendered one voice: the output rows (silent voices included, as zeros) are the partial sums,
+        // added in voice order by the same two reduction kernels
+        const uint32_t nv = (uint32_t)b->n_voices;
+        if (nv == 1) {
+            CUDA_TRY(cudaMemcpyAsync(d_bus_out, d_voice_out, frames * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
+        } else {
+            const size_t need = (size_t)s2::bus_segments(nv) * frames;
+            if (need > b->partials_cap) {
+                if (b->d_partials) CUDA_TRY(cudaFree(b->d_partials));
+                b->d_partials = nullptr; b->partials_cap = 0;
+                CUDA_TRY(cudaMalloc(&b->d_partials, need * sizeof(float)));
+                b->partials_cap = need;
+            }
+            CUDA_TRY(s2::launch_bus_reduce(d_voice_out, nv, row_stride, (uint32_t)frames, b->d_partials, d_bus_out, b->stream));
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+        }
+    }
     b->ts_step++;
     b->ts_blocks++;
     b->total_frames += frames;
@@ -370,7 +390,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     CUDA_TRY(cudaSetDevice(b->device));
     if (trace == s2::TRACE_NONE) {
         const int cls = ts_block_class(b, frames, d_voice_out, d_bus_out);
-        if (cls) return bank_render_time_split(b, frames, d_voice_out, row_stride, cls == 2);
+        if (cls) return bank_render_time_split(b, frames, d_voice_out, row_stride, d_bus_out, cls == 2);
     }
     b->ts_main_dirty = true;      // the general kernels below move the carried phase on the bank's stream
     if (b->n_sub > 1 && trace == s2::TRACE_NONE) return bank_render_pipelined(b, frames, d_voice_out, row_stride, d_bus_out);
@@ -411,7 +431,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     else CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
-        CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, (uint32_t)frames, partials + (size_t)n_warps * frames,
+        CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
                                        d_bus_out, b->stream));
         g_launches.fetch_add(2, std::memory_order_relaxed);
     }

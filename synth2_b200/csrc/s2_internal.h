@@ -67,9 +67,9 @@ cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t 
 // moving: some voice's cutoff follows a ramping mod envelope in this block (per-frame coefficients)
 cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, bool moving, const float* seg_phase,
                              cudaStream_t stream);
-// two kernels; seg_scratch holds bus_segments(n_warps) * frames floats
-cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
-                              float* bus, cudaStream_t stream);
+// two kernels; partial row w starts at partials + w * row_stride; seg_scratch holds bus_segments(n_warps) * frames floats
+cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, size_t row_stride, uint32_t frames,
+                              float* seg_scratch, float* bus, cudaStream_t stream);
 uint32_t bus_segments(uint32_t n_warps);
 // release_row[slot] = staged[voice_of_slot[slot]]  (bulk note-off table given in voice order)
 cudaError_t launch_gather_u32(const uint32_t* staged, const float* row_index_bits, uint32_t* dst_row,

@@ -510,7 +510,7 @@ render_kernel(const RenderArgs a) {
 constexpr uint32_t kBusSegWarps = 64;
 
 __global__ void __launch_bounds__(256) bus_reduce_stage1(const float* __restrict__ partials, uint32_t n_warps,
-                                                         uint32_t frames, float* __restrict__ seg) {
+                                                         size_t row_stride, uint32_t frames, float* __restrict__ seg) {
     __shared__ float sm[8][33];
     const uint32_t tx = threadIdx.x & 31u, sub = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x * 32u + tx;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) bus_reduce_stage1(const float* __restrict
     if (t < frames) {
         float v[8];
 #pragma unroll
-        for (uint32_t k = 0; k < 8u; k++) v[k] = (w0 + k < n_warps) ? partials[(size_t)(w0 + k) * frames + t] : 0.0f;
+        for (uint32_t k = 0; k < 8u; k++) v[k] = (w0 + k < n_warps) ? partials[(size_t)(w0 + k) * row_stride + t] : 0.0f;
         acc = v[0];
 #pragma unroll
         for (uint32_t k = 1; k < 8u; k++) acc = __fadd_rn(acc, v[k]);
@@ -593,11 +593,11 @@ cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, 
 
 uint32_t bus_segments(uint32_t n_warps) { return (n_warps + kBusSegWarps - 1) / kBusSegWarps; }
 
-cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, uint32_t frames, float* seg_scratch,
-                              float* bus, cudaStream_t stream) {
+cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, size_t row_stride, uint32_t frames,
+                              float* seg_scratch, float* bus, cudaStream_t stream) {
     if (frames == 0) return cudaSuccess;
     const uint32_t n_seg = bus_segments(n_warps);
-    bus_reduce_stage1<<<dim3((frames + 31) / 32, n_seg), 256, 0, stream>>>(partials, n_warps, frames, seg_scratch);
+    bus_reduce_stage1<<<dim3((frames + 31) / 32, n_seg), 256, 0, stream>>>(partials, n_warps, row_stride, frames, seg_scratch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     bus_reduce_stage2<<<(frames + 255) / 256, 256, 0, stream>>>(seg_scratch, n_seg, frames, bus);

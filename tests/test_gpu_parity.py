@@ -712,6 +712,28 @@ def test_time_split_biquad_2x2_scan():
     assert float(np.median(d)) <= 2e-5
 
 
+def test_time_split_mix_is_the_sum_of_the_rows():
+    """With rows and a mix requested, a time-split block sums its output rows in voice order (two reduction
+    kernels, fixed tree); against the oracle's sequential sum within the bus tolerance."""
+    V, T = 300, 2048
+    v = bank_for(0, V, 8 * T, mod_to_lpf_choices=(0.0,))
+    v["active"][11::13] = 0
+    ref, rbus, _ = oracle_bank_render(v, 0, [T, T])
+    with s2.VoiceBank(v, SR, 0) as bank:
+        bank.set_time_split(True)
+        rows = torch.empty((V, T + 8), device="cuda", dtype=torch.float32)
+        bus = torch.empty(2 * T, device="cuda", dtype=torch.float32)
+        for i in range(2):
+            bank.render(T, rows, T + 8, bus[i * T:(i + 1) * T])
+        bank.sync()
+        assert bank.time_split_blocks == 2
+    got = bus.cpu().numpy()
+    scale = max(1.0, float(np.max(np.abs(rbus))))
+    assert float(np.max(np.abs(got - rbus))) <= TOL_ABS * scale
+    last = rows[:, :T].double().sum(dim=0).cpu().numpy()
+    assert float(np.max(np.abs(got[T:] - last))) <= 1e-5 * scale
+
+
 def test_time_split_argument_errors():
     with s2.VoiceBank(bank_for(0, 64, 48000), SR, 0) as bank:
         bank.set_time_split(True)
@@ -895,7 +917,7 @@ def test_no_write_outside_the_output_rows(mode, V, frames):
         if mode == "time_split":
             bank.set_time_split(True)
         for _ in range(2):
-            bank.render(frames, buf[1:], stride, None if mode == "time_split" else bus[32:])
+            bank.render(frames, buf[1:], stride, bus[32:])
         bank.sync()
         if mode == "time_split":
             assert bank.time_split_blocks == 2
@@ -905,8 +927,7 @@ def test_no_write_outside_the_output_rows(mode, V, frames):
     assert np.all(np.isfinite(out[1:-1, :frames])) and not np.any(out[1:-1, :frames] == -777.0)
     b = bus.cpu().numpy()
     assert np.all(b[:32] == -777.0) and np.all(b[32 + frames:] == -777.0)
-    if mode != "time_split":
-        assert not np.any(b[32:32 + frames] == -777.0)
+    assert not np.any(b[32:32 + frames] == -777.0)
 
 
 # ------------------------------------------------------------------------------ the rest of dsp_filters.rs
