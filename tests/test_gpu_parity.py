@@ -997,3 +997,48 @@ def test_compiled_example_renders_like_the_python_mirror(tmp_path):
     want = syn.render_score(p.events, 24000, SR)
     syn.close()
     assert got.tobytes() == want.tobytes()
+
+
+def test_time_split_with_note_events_between_blocks():
+    """release_voice / set_releases / set_voice between time-split blocks: the host's view of the voices (which
+    decides whether a block qualifies and whether its cutoff moves) follows every edit."""
+    V, T = 64, 2048
+    v = bank_for(0, V, 16 * T)
+    v["release_offset"] = s2.NO_RELEASE
+    v["mod_sustain"] = 0.5
+    v["mod_release_ms"] = 15.0
+    ref_v = v.copy()
+    st = oracle.bank_init_states(ref_v)
+    outs_ref, outs = [], []
+    with s2.VoiceBank(v, SR, 0) as bank:
+        bank.set_time_split(True)
+
+        def block():
+            o, _ = oracle.bank_render(ref_v, st, SR, 0, T, want_bus=False)
+            outs_ref.append(o)
+            vo = torch.empty((V, T), device="cuda", dtype=torch.float32)
+            bank.render(T, vo, T, None)
+            bank.sync()
+            outs.append(vo.cpu().numpy())
+
+        for _ in range(6):                       # decay (moving cutoff), then sustain
+            block()
+        bank.release_voice(5)                    # note_off of one voice at frame 12,288
+        ref_v["release_offset"][5] = 6 * T
+        block()
+        rel = np.full(V, s2.NO_RELEASE, dtype=np.uint32)
+        rel[::2] = 7 * T + 100                   # bulk note-off table: half the voices, mid-block
+        rel[5] = 6 * T
+        bank.set_releases(rel)
+        ref_v["release_offset"] = rel
+        block(); block()
+        nv = bank_for(0, 1, 16 * T)[0:1].copy()  # a new note in slot 9
+        nv["pitch_hz"] = 523.25
+        bank.set_voice(9, nv)
+        ref_v[9] = nv[0]
+        st[9] = oracle.bank_init_states(nv)[0]
+        block(); block()
+        assert bank.time_split_blocks == 11
+        gst = bank.get_state()
+    assert_parity(np.concatenate(outs_ref, axis=1), np.concatenate(outs, axis=1), "time-split with events")
+    assert_state_parity(gst, st, 0)
