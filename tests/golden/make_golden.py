@@ -24,6 +24,9 @@ from synth2_b200 import bankgen  # noqa: E402
 SR = 48000
 EVENTS = [(0, "on", 69), (96000, "on", 57), (192000, "on", 76), (240000, "off", 69), (336000, "off", 57), (336000, "off", 76)]
 TOTAL = 480000
+# filter kinds: one-pole, then dsp_filters.rs low-pass / high-pass / band-pass / first-order low- and high-pass
+BANK_FIXTURES = ((0, "bank_small_onepole"), (1, "bank_small_biquad"), (2, "bank_small_biquad_hp"),
+                 (3, "bank_small_biquad_bp"), (4, "bank_small_first_lp"), (5, "bank_small_first_hp"))
 WINDOWS = [0, 4800, 9600, 96000, 192000, 240000, 244800, 336000, 340800, 479936]   # 64-frame windows
 
 
@@ -47,9 +50,11 @@ def main():
         stride_samples=buf[::4801].copy(), crc32=np.uint32(zlib.crc32(buf.tobytes())),
         sum=np.float64(buf.astype(np.float64).sum()), sumsq=np.float64((buf.astype(np.float64) ** 2).sum()),
         peak=np.float32(np.abs(buf).max()))
-    for fk, name in ((0, "bank_small_onepole"), (1, "bank_small_biquad")):
+    for fk, name in BANK_FIXTURES:
         sweep = bankgen.MOD_TO_LPF_BIQUAD if fk else bankgen.MOD_TO_LPF_ONE_POLE
         v = bankgen.make_bank(16, 2048, kinds=(0, 1, 2, 3), mod_to_lpf_choices=sweep)
+        if fk == 3:
+            v["damping"] += 2.0        # the band-pass reads the field as its quality factor
         v["noise_amt"] = (np.arange(16) % 3) * 0.25
         v["osc_gain"] = 0.5 + (np.arange(16) % 4) * 0.125
         v["release_offset"] = 640

@@ -7,7 +7,9 @@ import numpy as np
 import pytest
 
 import oracle
-from golden.make_golden import EVENTS, SR, TOTAL, render_config1
+from golden.make_golden import BANK_FIXTURES, EVENTS, SR, TOTAL, render_config1
+
+BANK_NAMES = [name for _, name in BANK_FIXTURES]
 
 G = pathlib.Path(__file__).resolve().parent / "golden"
 
@@ -22,7 +24,7 @@ def test_oracle_reproduces_config1_fixture():
     assert float(np.abs(buf).max()) == float(g["peak"]) > 0.1
 
 
-@pytest.mark.parametrize("name", ["bank_small_onepole", "bank_small_biquad"])
+@pytest.mark.parametrize("name", BANK_NAMES)
 def test_oracle_reproduces_bank_fixture(name):
     g = np.load(G / f"{name}.npz")
     v = g["voices"]
@@ -54,7 +56,7 @@ def test_gpu_matches_config1_fixture():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["bank_small_onepole", "bank_small_biquad"])
+@pytest.mark.parametrize("name", BANK_NAMES)
 def test_gpu_matches_bank_fixture(name):
     import torch
     import synth2_b200 as s2
