@@ -183,6 +183,19 @@ def test_sweep_bank_is_the_config5_grid():
         bankgen.make_sweep_bank(0, 480000, first_variant=32768, n_variants=1)
 
 
+def test_sweep_banks_of_different_gpus_differ_only_in_the_note():
+    """Config 5 shards by GPU index with no exchange: rank g renders the same 32 x 32 x 32 grid at note 48 + 4 g."""
+    a, b = bankgen.make_sweep_bank(0, 480000, n_variants=2048), bankgen.make_sweep_bank(3, 480000, n_variants=2048)
+    for f in a.dtype.names:
+        if f == "pitch_hz":
+            ratio = b[f].astype(np.float64) / a[f].astype(np.float64)
+            assert np.allclose(ratio, 2.0 ** (12 / 12.0), rtol=1e-6)          # 3 GPUs x 4 semitones = one octave
+        else:
+            assert np.array_equal(a[f], b[f]), f
+    with pytest.raises(ValueError):
+        bankgen.make_sweep_bank(20, 480000)                                  # note 128 does not exist
+
+
 def test_splitmix64_known_answer():
     # splitmix64 reference stream for seed 0: first output
     assert int(bankgen.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
