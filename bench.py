@@ -133,9 +133,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the port of the reference path (oracle/) on the host cores
 
-def cpu_port_throughput(voices_desc, n_threads, frames, repeats=1):
+_ORACLE_FLAGS = None
+
+
+def cpu_oracle():
+    """The C port of the reference path, built for this host (oracle/Makefile `native`)."""
+    global _ORACLE_FLAGS
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle
+    if _ORACLE_FLAGS is None:
+        _ORACLE_FLAGS = oracle.use_native_build()
+    return oracle
+
+
+def cpu_port_throughput(voices_desc, n_threads, frames, repeats=1):
+    oracle = cpu_oracle()
     best = None
     for _ in range(repeats):
         st = oracle.bank_init_states(voices_desc)
@@ -159,7 +171,7 @@ def cpu_baseline(args, bankgen):
     rate, dt = cpu_port_throughput(sample, cores, frames)
     return {"value": rate, "unit": "voice-samples/s", "cores": cores, "kind": "port",
             "sample": f"{nv} voices x {frames} frames of the config-3 bank (biquad+ADSR), {dt:.1f} s, "
-                      f"{cores} threads; C port of the reference's x16 path (Rust toolchain absent)"}
+                      f"{cores} threads; C port of the reference's x16 path (Rust toolchain absent), gcc {_ORACLE_FLAGS}"}
 
 
 # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to stdout at
@@ -195,8 +207,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     nv = max(cores * 64, 1024)          # enough voices per thread that thread start-up does not show (same as cpu_baseline)
     voices = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
-    sys.path.insert(0, str(ROOT / "tests"))
-    import oracle
+    oracle = cpu_oracle()
     st = oracle.bank_init_states(voices)
     frames = step_frames(args.steps, args.block)
     for _ in range(args.warmup):
@@ -207,7 +218,8 @@ def run_reference(args):
         oracle.bank_render(voices, st, SR, FILTER_BIQUAD, fr, want_voices=False, want_bus=False, nthreads=cores)
     dt = time.perf_counter() - t0
     value = nv * sum(frames) / dt
-    sample = f"{nv} voices x {sum(frames)} frames of the config-3 bank per run, {cores} threads, C port of the reference x16 path"
+    sample = (f"{nv} voices x {sum(frames)} frames of the config-3 bank per run, {cores} threads, C port of the reference "
+              f"x16 path, gcc {_ORACLE_FLAGS}")
     emit({
         "impl": "reference", "metric": "voice-samples/sec (osc+biquad, 48 kHz)", "value": value,
         "unit": "voice-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

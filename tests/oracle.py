@@ -65,6 +65,22 @@ _SIGS = {
 _lib = None
 
 
+def use_native_build():
+    """bench.py only: time the CPU baseline on a build tuned for THIS host (`make -C oracle native`: -O3
+    -march=native, same IEEE semantics).  Falls back to the portable library when it cannot be built.
+    Returns the flags description for the bench line."""
+    global _lib, SO
+    native = ROOT / "oracle" / "libs2oracle_native.so"
+    try:
+        native.unlink(missing_ok=True)          # a copy built on another host may use other instructions
+        subprocess.run(["make", "-C", str(native.parent), "native"], check=True, capture_output=True)
+        C.CDLL(str(native))
+        SO, _lib = native, None
+        return "-O3 -march=native -ffp-contract=off"
+    except Exception:
+        return "-O2 -march=x86-64-v3 -ffp-contract=off"
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -346,3 +346,25 @@ def test_dsp_filters_match_a_binary64_restatement(kind, freq, dq):
     # the responses the names promise: DC passes a low-pass, is blocked by a high-pass and a band-pass
     dc = got[200:256].mean()
     assert abs(dc - (1.0 if kind in ("lp2", "lp1") else 0.0)) < 2e-3
+
+
+def test_host_tuned_baseline_build_gives_the_same_bits():
+    """bench.py times the CPU baseline on `make -C oracle native` (-O3 -march=native): same source, contraction
+    off, no fast-math — it must render exactly what the portable build renders."""
+    from synth2_b200 import bankgen
+    v = bankgen.make_bank(24, 4096, kinds=(0, 1, 2, 3), mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
+    outs = []
+    so, handle = oracle.SO, oracle._lib
+    try:
+        for native in (False, True):
+            if native:
+                flags = oracle.use_native_build()
+                if "native" not in flags:
+                    pytest.skip("no compiler for the host-tuned build")
+            for fk in (0, 1):
+                st = oracle.bank_init_states(v)
+                o, b = oracle.bank_render(v, st, 48000, fk, 1000)
+                outs.append((o.tobytes(), b.tobytes(), st.tobytes()))
+    finally:
+        oracle.SO, oracle._lib = so, handle
+    assert outs[0] == outs[2] and outs[1] == outs[3]
