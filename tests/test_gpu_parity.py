@@ -1042,3 +1042,38 @@ def test_time_split_with_note_events_between_blocks():
         gst = bank.get_state()
     assert_parity(np.concatenate(outs_ref, axis=1), np.concatenate(outs, axis=1), "time-split with events")
     assert_state_parity(gst, st, 0)
+
+
+@pytest.mark.timeout(120)
+def test_player_lifecycle_stress():
+    """Create / start / play / free many players in a row, with notes posted from another thread while the audio
+    callback drains: no hang, no lost buffer, underruns only while nothing was rendered yet."""
+    import threading
+    for round_ in range(8):
+        pl = s2.Player(SR, start=(round_ % 2 == 0))
+        stop = threading.Event()
+
+        def poster():
+            k = 0
+            while not stop.is_set():
+                pl.note_on(40 + (k % 40))
+                if k % 3 == 2:
+                    pl.note_off(40 + ((k - 2) % 40))
+                k += 1
+
+        t = threading.Thread(target=poster)
+        t.start()
+        if round_ % 2:
+            pl.start()
+        out = np.zeros((512, 2), np.float32)
+        got = 0
+        for _ in range(24):
+            got += pl.fill(out)
+            assert np.all(np.isfinite(out))
+        stop.set()
+        t.join()
+        st = pl.stats()
+        assert st["frames_played"] == got
+        assert st["buffers_rendered"] >= got // s2.player.BUFFER_FRAMES
+        pl.close()
+        pl.close()                                 # idempotent
