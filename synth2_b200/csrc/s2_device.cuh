@@ -543,6 +543,7 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
     const float2 ts1_2 = make_float2(F.ts1, F.ts1), ts2_2 = make_float2(F.ts2, F.ts2);
     const float2 gain2 = make_float2(F.gain, F.gain), namt2 = make_float2(F.namt, F.namt);
     const float2 ey0_2 = make_float2(F.ey0, F.ey0);
+    const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);               // (P / 2) * 2^60, exact
     uint32_t n = n0;
     float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
     EnvP A;
@@ -576,10 +577,13 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             if (KIND == 1) {
                 osc2 = pfma2(slope2, x2, one2);
             } else if (KIND == 0) {
-                // scalar adds: x2 is a packed product (contraction hazard above)
-                const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
-                osc2.x = __uint_as_float((__float_as_uint(dl.x) & 0x80000000u) ^ 0xbf800000u);
-                osc2.y = __uint_as_float((__float_as_uint(dl.y) & 0x80000000u) ^ 0xbf800000u);
+                // x < P/2 ? +1 : -1 without a compare or bit surgery: s = sat(2^60 * (P/2 - x)) is exactly 1 when
+                // x < P/2 and exactly 0 otherwise (the fma is exact in sign; two distinct binary32 values of this
+                // magnitude differ by >= 2^-24, so the product is >= 2^36 before the clamp; equality gives +0; a
+                // NaN clamps to 0, i.e. -1, as `NaN < h` is false), and 2 s - 1 is exact.
+                const float2 sq = make_float2(__saturatef(__fmaf_rn(x2.x, -0x1p60f, hbig)),
+                                              __saturatef(__fmaf_rn(x2.y, -0x1p60f, hbig)));
+                osc2 = pfma2(sq, two2, none2);
             } else if (KIND == 2) {
                 const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
                 const float2 a = pfma2(ts1_2, x2, one2);
