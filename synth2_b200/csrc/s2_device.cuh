@@ -531,8 +531,8 @@ __device__ __forceinline__ void chunk_fast(FastV<NV>& F, const uint32_t (&kind)[
 // recurrences (phase, filter) stay scalar — a packed op has twice the latency — while everything that
 // is feed-forward (waveform, noise map, gain/noise combine, envelope, output gain) is computed for
 // frames (i, i+1) of the voice in one packed instruction.  Element-wise rounding is identical.
-// ALIGNED8: the voice's frame offset is a multiple of 8 at every 8-frame trip, so offset + i == offset ^ i
-// and the noise hash input of frame i is one LOP3 with an immediate.
+// ALIGNED8: the voice's frame offset and its rotated seed are multiples of 8 (seeds below 2^27 rotate to multiples
+// of 32), so (seed' ^ (offset + i)) == (seed' ^ offset) + i and the hash of frame i is one add with an immediate.
 // GCONST = false: the amp envelope is evaluated per frame with its full stage chain (env_x16), so
 // attack / decay / release ramps and their boundaries stay on the fast path.
 template <int FILTER, int KIND, bool GCONST, bool NAMT0, bool ALIGNED8, int TRACE>
@@ -558,6 +558,9 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
 #pragma unroll 1
     for (int jt = 0; jt < kChunk / S2_TRIP; jt++) {
     const uint32_t nb = rot ^ n;                                  // hash input base of this trip
+    // ALIGNED8 (offset and rot both multiples of 8): nb ^ i == nb + i for i < 8, so the hash of frame i is
+    // nb * C + i * C: one multiply per trip and one add with an immediate per frame
+    const uint32_t nbc = nb * 0x9e3779b9u;
 #pragma unroll
     for (int jj = 0; jj < S2_TRIP / 4; jj++) {
         const int j = (S2_TRIP / 4) * jt + jj;
@@ -615,8 +618,8 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
             }
             // ---- noise (try3/hashnoise.rs:33-68)
             const uint32_t fi = 4u * jj + 2u * h;                 // frame index inside the trip (compile-time)
-            const uint32_t ha = (ALIGNED8 ? (nb ^ fi) : (rot ^ (n + fi))) * 0x9e3779b9u;
-            const uint32_t hb = (ALIGNED8 ? (nb ^ (fi + 1u)) : (rot ^ (n + fi + 1u))) * 0x9e3779b9u;
+            const uint32_t ha = ALIGNED8 ? nbc + fi * 0x9e3779b9u : (rot ^ (n + fi)) * 0x9e3779b9u;
+            const uint32_t hb = ALIGNED8 ? nbc + (fi + 1u) * 0x9e3779b9u : (rot ^ (n + fi + 1u)) * 0x9e3779b9u;
             const float2 v2 = make_float2(__uint2float_rn(ha & 0xffffu), __uint2float_rn(hb & 0xffffu));
             const float2 q2 = pfma2(v2, make_float2(0x1.0001p-16f, 0x1.0001p-16f),
                                          pmul2(v2, make_float2(0x1.0001p-48f, 0x1.0001p-48f)));

@@ -130,7 +130,7 @@ render_kernel(const RenderArgs a) {
     for (int e = 0; e < NV; e++) {
         lane_any_active |= active[e];
         lane_namt0 &= !active[e] || __float_as_uint(vget(F.namt, e)) == 0u;      // +0.0 only
-        lane_al8 &= !active[e] || (n[e] & (uint32_t)(S2_TRIP - 1)) == 0u;
+        lane_al8 &= !active[e] || ((n[e] | rot[e]) & (uint32_t)(S2_TRIP - 1)) == 0u;
     }
     const uint32_t amask = __ballot_sync(0xffffffffu, lane_any_active);
     int wkind = -1;
