@@ -196,6 +196,44 @@ render_kernel(const RenderArgs a) {
     uint32_t fast_left = 0, gc_left = 0;
     bool nv2_gconst = false;
 
+    // Runs of fast tiles.  A third of the warp's stall time sits at the chunk boundaries (loop control, dispatch,
+    // store-variant selection: uniform-datapath code with exposed latencies, and the warps of an SM reach it in
+    // lockstep), so when the store has its simple launch-uniform form — every tile row has an output row or no
+    // rows are wanted, and the mix, if any, is the per-warp partial of a wide bank — the fast path renders up to
+    // kRunTiles tiles per trip round the outer loop, each followed by its own straight-line write-back.
+    constexpr uint32_t kRunTiles = 4;
+    const bool bus_wide_ok = a.bus_partials != nullptr && a.n_voices > 32u && (frames & 3u) == 0u &&
+                             (reinterpret_cast<uintptr_t>(a.bus_partials) & 15u) == 0u;
+    const bool simple_store = NV == 1 && (gout == nullptr || all_rows) && (a.bus_partials == nullptr || bus_wide_ok) &&
+                              (gout != nullptr || a.bus_partials != nullptr);
+    auto store_simple = [&](uint32_t ts) {
+        const size_t tb = ((size_t)ts + (size_t)c4) * sizeof(float);
+        if (a.bus_partials == nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
+                const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                __stcs(reinterpret_cast<float4*>(dst + tb), val);
+            }
+        } else {
+            float4 val[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
+                if (gout) __stcs(reinterpret_cast<float4*>(reinterpret_cast<char*>(rp[4 * i + q]) + tb), val[i]);
+            }
+            float2 s01, s23;
+            tree_sum_rows<8>(val, s01, s23);
+#pragma unroll
+            for (int sh = 8; sh <= 16; sh <<= 1) {
+                s01 = padd2(s01, make_float2(__shfl_xor_sync(0xffffffffu, s01.x, sh), __shfl_xor_sync(0xffffffffu, s01.y, sh)));
+                s23 = padd2(s23, make_float2(__shfl_xor_sync(0xffffffffu, s23.x, sh), __shfl_xor_sync(0xffffffffu, s23.y, sh)));
+            }
+            float* gb = a.bus_partials + (size_t)(a.slot_begin / (uint32_t)kRows + blockIdx.x * (uint32_t)kWarpsPerBlock + (uint32_t)warp) * a.frames;
+            if (lane < 8) *reinterpret_cast<float4*>(gb + ts + c4) = make_float4(s01.x, s01.y, s23.x, s23.y);
+        }
+    };
+
     for (uint32_t t0 = 0; t0 < frames; t0 += kChunk) {
         const uint32_t cnt = min((uint32_t)kChunk, frames - t0);
         const bool full = cnt == kChunk && t0 + kChunk <= f16;
@@ -309,17 +347,40 @@ render_kernel(const RenderArgs a) {
 
         if (warp_fast) {
             // inactive voices run the same code on zeroed constants; their rows are cleared below
-            fast_left -= kChunk;
-            gc_left = gc_left >= (uint32_t)kChunk ? gc_left - kChunk : 0u;
-            switch (wkind) {
-            case 0: chunk_fast_dispatch<NV, FILTER, 0, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
-            case 1: chunk_fast_dispatch<NV, FILTER, 1, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
-            case 2: chunk_fast_dispatch<NV, FILTER, 2, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
-            case 3: chunk_fast_dispatch<NV, FILTER, 3, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
-            default: chunk_fast_dispatch<NV, FILTER, -1, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+            uint32_t reps = 1;
+            if (simple_store) {
+                uint32_t room = min(fast_left, f16 - t0) / (uint32_t)kChunk;      // >= 1: warp_fast
+                if (gconst) room = min(room, gc_left / (uint32_t)kChunk);          // >= 1: gconst
+                reps = min(room, kRunTiles);
             }
+            for (uint32_t r = 0;;) {
+                switch (wkind) {
+                case 0: chunk_fast_dispatch<NV, FILTER, 0, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+                case 1: chunk_fast_dispatch<NV, FILTER, 1, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+                case 2: chunk_fast_dispatch<NV, FILTER, 2, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+                case 3: chunk_fast_dispatch<NV, FILTER, 3, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+                default: chunk_fast_dispatch<NV, FILTER, -1, TRACE>(gconst, namt0, aligned8, F, &cold(0).L.amp, kind, rot, n, tile, lane, sintab); break;
+                }
 #pragma unroll
-            for (int e = 0; e < NV; e++) n[e] += kChunk;
+                for (int e = 0; e < NV; e++) n[e] += kChunk;
+                if (!simple_store) break;                    // one tile, written back by the common code below
+                if (!active[0]) {
+                    float* row = tile + lane * kTileStride;
+#pragma unroll
+                    for (int j = 0; j < kChunk / 4; j++)
+                        *reinterpret_cast<float4*>(row + 4 * j) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                __syncwarp();
+                store_simple(t0 + r * (uint32_t)kChunk);
+                __syncwarp();      // every lane is done reading the tile before the next one overwrites it
+                if (++r == reps) break;
+            }
+            fast_left -= reps * (uint32_t)kChunk;
+            gc_left = gc_left >= reps * (uint32_t)kChunk ? gc_left - reps * (uint32_t)kChunk : 0u;
+            if (simple_store) {
+                t0 += (reps - 1u) * (uint32_t)kChunk;        // the loop header adds the last tile
+                continue;
+            }
         } else if (warp_semi) {
             if constexpr (NV == 1) {
                 // voices that are fully constant run the same code: their cutoff simply does not move
