@@ -275,7 +275,7 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
         } else {
             CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
                                            d_bus_out, b->mix));
-            g_launches.fetch_add(2, std::memory_order_relaxed);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         CUDA_TRY(cudaEventRecord(b->ev_mix[p], b->mix));
     }
@@ -353,7 +353,7 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     g_launches.fetch_add(2, std::memory_order_relaxed);
     if (d_bus_out) {
         // one warp rendered one voice: the output rows (silent voices included, as zeros) are the partial sums,
-        // added in voice order by the same two reduction kernels
+        // added by the same reduction kernel
         const uint32_t nv = (uint32_t)b->n_voices;
         if (nv == 1) {
             CUDA_TRY(cudaMemcpyAsync(d_bus_out, d_voice_out, frames * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
@@ -366,7 +366,7 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
                 b->partials_cap = need;
             }
             CUDA_TRY(s2::launch_bus_reduce(d_voice_out, nv, row_stride, (uint32_t)frames, b->d_partials, d_bus_out, b->stream));
-            g_launches.fetch_add(2, std::memory_order_relaxed);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
         }
     }
     b->ts_step++;
@@ -433,7 +433,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     if (d_bus_out && n_warps > 1) {
         CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
                                        d_bus_out, b->stream));
-        g_launches.fetch_add(2, std::memory_order_relaxed);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     b->total_frames += frames;
     b->max_offset += frames;

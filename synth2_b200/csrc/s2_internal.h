@@ -67,7 +67,7 @@ cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t 
 // moving: some voice's cutoff follows a ramping mod envelope in this block (per-frame coefficients)
 cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, bool moving, const float* seg_phase,
                              cudaStream_t stream);
-// two kernels; partial row w starts at partials + w * row_stride; seg_scratch holds bus_segments(n_warps) * frames floats
+// one kernel, fixed summation order; partial row w starts at partials + w * row_stride (seg_scratch is unused)
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, size_t row_stride, uint32_t frames,
                               float* seg_scratch, float* bus, cudaStream_t stream);
 uint32_t bus_segments(uint32_t n_warps);

@@ -565,47 +565,47 @@ render_kernel(const RenderArgs a) {
     }
 }
 
-// Bus reduction, two stages, fixed summation tree (deterministic):
-//   stage 1  block (fx, sy) adds the 64 per-warp partial rows [64*sy, 64*sy + 64) for 32 frames: 8 threads
-//            per frame take 8 rows each (independent loads, index order), then the 8 sums are added in
-//            order -> seg[sy][t].  4,096 blocks at the bench shape: bandwidth-bound instead of the
-//            latency-bound single pass it replaces (51 us -> ~10 us for 32 MB of partials).
-//   stage 2  bus[t] = seg[0][t] + seg[1][t] + ... in order (n_seg <= a few dozen, L2-resident).
-// Reads are coalesced over t (128 bytes per row per warp).
-constexpr uint32_t kBusSegWarps = 64;
+// Bus reduction: one kernel, fixed summation order (deterministic).  Block fx owns 32 frames; its 8 warps take the
+// partial rows w, w + 8, w + 16, ... (lane = frame: 128-byte coalesced reads), each with four accumulators over
+// consecutive rows of its sequence, eight loads in flight; the eight warp sums are then added in order.
+// Few, long-lived blocks on purpose: the reduction runs next to the render kernels of the following step on a
+// machine whose every slot is taken by long-running render blocks.  The 4,096 short blocks of the two-stage
+// form it replaces queued for those slots one by one and cost ~30 us of step time for 19 us of work; 128 blocks
+// of 8 warps need one slot each and displace next to nothing (it is latency-bound at ~20 us, off the critical path).
+constexpr uint32_t kBusSegWarps = 64;      // (scratch sizing of the callers: segments of the former first stage)
 
-__global__ void __launch_bounds__(256) bus_reduce_stage1(const float* __restrict__ partials, uint32_t n_warps,
-                                                         size_t row_stride, uint32_t frames, float* __restrict__ seg) {
+__global__ void __launch_bounds__(256) bus_reduce_kernel(const float* __restrict__ partials, uint32_t n_rows,
+                                                         size_t row_stride, uint32_t frames, float* __restrict__ bus) {
     __shared__ float sm[8][33];
-    const uint32_t tx = threadIdx.x & 31u, sub = threadIdx.x >> 5;
+    const uint32_t tx = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x * 32u + tx;
-    const uint32_t w0 = blockIdx.y * kBusSegWarps + sub * 8u;
-    float acc = 0.0f;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     if (t < frames) {
-        float v[8];
+        const float* __restrict__ col = partials + t;
+        uint32_t r = w;
+        for (; r + 56u < n_rows; r += 64u) {                  // rows r, r+8, ..., r+56: eight loads in flight
+            float v[8];
 #pragma unroll
-        for (uint32_t k = 0; k < 8u; k++) v[k] = (w0 + k < n_warps) ? partials[(size_t)(w0 + k) * row_stride + t] : 0.0f;
-        acc = v[0];
-#pragma unroll
-        for (uint32_t k = 1; k < 8u; k++) acc = __fadd_rn(acc, v[k]);
+            for (uint32_t k = 0; k < 8u; k++) v[k] = col[(size_t)(r + 8u * k) * row_stride];
+            a0 = __fadd_rn(a0, v[0]); a1 = __fadd_rn(a1, v[1]); a2 = __fadd_rn(a2, v[2]); a3 = __fadd_rn(a3, v[3]);
+            a0 = __fadd_rn(a0, v[4]); a1 = __fadd_rn(a1, v[5]); a2 = __fadd_rn(a2, v[6]); a3 = __fadd_rn(a3, v[7]);
+        }
+        for (uint32_t k = 0; r < n_rows; r += 8u, k++) {     // the rest, same rotation over the accumulators
+            const float v = col[(size_t)r * row_stride];
+            if ((k & 3u) == 0u) a0 = __fadd_rn(a0, v);
+            else if ((k & 3u) == 1u) a1 = __fadd_rn(a1, v);
+            else if ((k & 3u) == 2u) a2 = __fadd_rn(a2, v);
+            else a3 = __fadd_rn(a3, v);
+        }
     }
-    sm[sub][tx] = acc;
+    sm[w][tx] = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
     __syncthreads();
-    if (sub == 0 && t < frames) {
+    if (w == 0 && t < frames) {
         float total = sm[0][tx];
 #pragma unroll
         for (int k = 1; k < 8; k++) total = __fadd_rn(total, sm[k][tx]);
-        seg[(size_t)blockIdx.y * frames + t] = total;
+        bus[t] = total;
     }
-}
-
-__global__ void bus_reduce_stage2(const float* __restrict__ seg, uint32_t n_seg, uint32_t frames,
-                                  float* __restrict__ bus) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= frames) return;
-    float acc = seg[t];
-    for (uint32_t k = 1; k < n_seg; k++) acc = __fadd_rn(acc, seg[(size_t)k * frames + t]);
-    bus[t] = acc;
 }
 
 __global__ void gather_u32_kernel(const uint32_t* __restrict__ staged, const float* __restrict__ row_index_bits,
@@ -659,13 +659,9 @@ cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, 
 uint32_t bus_segments(uint32_t n_warps) { return (n_warps + kBusSegWarps - 1) / kBusSegWarps; }
 
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, size_t row_stride, uint32_t frames,
-                              float* seg_scratch, float* bus, cudaStream_t stream) {
+                              float* /*seg_scratch*/, float* bus, cudaStream_t stream) {
     if (frames == 0) return cudaSuccess;
-    const uint32_t n_seg = bus_segments(n_warps);
-    bus_reduce_stage1<<<dim3((frames + 31) / 32, n_seg), 256, 0, stream>>>(partials, n_warps, row_stride, frames, seg_scratch);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    bus_reduce_stage2<<<(frames + 255) / 256, 256, 0, stream>>>(seg_scratch, n_seg, frames, bus);
+    bus_reduce_kernel<<<(frames + 31) / 32, 256, 0, stream>>>(partials, n_warps, row_stride, frames, bus);
     return cudaGetLastError();
 }
 
