@@ -48,9 +48,11 @@ def timed(stream, bank, body):
 
 def report(name, voices, frames, seconds, **extra):
     vs = voices * frames / seconds
-    print(json.dumps({"rank": RANK, "config": name, "voices": voices, "frames_per_voice": frames, "seconds": seconds,
+    # one write per line: the ranks of a torchrun share this stdout
+    sys.stdout.write(json.dumps({"rank": RANK, "config": name, "voices": voices, "frames_per_voice": frames, "seconds": seconds,
                       "voice_samples_per_s": vs, "hbm_GBs": vs * 4 / 1e9, "frac_of_measured_hbm": vs * 4 / 1e9 / peak_gbs(),
-                      **extra}), flush=True)
+                      **extra}) + "\n")
+    sys.stdout.flush()
 
 
 def config2(stream):
