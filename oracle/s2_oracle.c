@@ -76,12 +76,14 @@ float s2o_hash_noise(uint32_t seed, float offset) {
 }
 
 /* NOT a reference function: the division-free form of the noise map used by the CUDA kernel
-   (synth2_b200/csrc/s2_kernels.cu noise_fast).  Kept here so a CPU-only test can prove it equal to
+   (synth2_b200/csrc/s2_device.cuh noise_fast).  Kept here so a CPU-only test can prove it equal to
    s2o_hash_noise for all 65,536 possible 16-bit hash values. */
 float s2o_noise_fast_form(uint32_t seed, uint32_t n) {
     uint32_t hash = s2o_hash_word(seed, n);
     float v = (float)(hash & 0xffffu);
-    float q = fmaf(v, 0x1.0001p-16f, v * 0x1.0001p-48f);
+    /* v * 0x1.0001p-16 is exact inside the fma and lies less than 2^-32 below v / 65535 with no rounding boundary
+       in between unless it sits on one (a tie): the tiny addend resolves those upwards, as the quotient would be */
+    float q = fmaf(v, 0x1.0001p-16f, 0x1p-45f);
     return fmaf(q, 2.0f, -1.0f);
 }
 

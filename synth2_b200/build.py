@@ -12,9 +12,10 @@ import sys
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libs2cuda.so"
-SOURCES = [CSRC / "s2_kernels.cu", CSRC / "s2_kernel_pc.cu", CSRC / "s2_kernel_ts.cu", CSRC / "s2_capi.cu",
+SOURCES = [CSRC / "s2_kernels.cu", CSRC / "s2_kernel_ts.cu", CSRC / "s2_capi.cu",
            CSRC / "s2_patch.cpp", CSRC / "s2_player.cpp"]
-DEPS = SOURCES + [CSRC / "s2_internal.h", CSRC / "s2_device.cuh", CSRC / "s2_math.h", CSRC / "sin_table_bits.inc",
+DEPS = SOURCES + [CSRC / "s2_internal.h", CSRC / "s2_device.cuh", CSRC / "s2_math.h", CSRC / "s2_cutoff.h",
+                  CSRC / "sin_table_bits.inc",
                   PKG.parent / "include" / "s2_cuda.h"]
 
 # -fmad=false / -prec-div / -prec-sqrt / -ftz=false: the render arithmetic is specified as

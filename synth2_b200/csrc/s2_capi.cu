@@ -149,14 +149,13 @@ struct s2_bank {
     size_t bus_cap = 0;          // floats
     std::vector<VoiceBook> book;  // indexed by voice
     // "Slots": device arrays are indexed by slot, not by the caller's voice index.  Banks wider than
-    // one warp are sorted by (active, oscillator kind) at creation so that the 32 lanes of a warp run
-    // the same oscillator code (kind-uniform warps take the straight-line specialised loop); output
+    // one warp are sorted by (active, oscillator kind, what follows the mod envelope, when the envelopes
+    // rest) at creation so that the 32 lanes of a warp run the same code for as long as possible; output
     // rows, state get/set and per-voice calls keep the caller's indices.  Banks of <= 32 voices keep
     // the identity order, which also keeps the bus sum in the reference's voice order.
     std::vector<uint32_t> slot_of_voice, voice_of_slot;
     bool identity = true;
-    bool pc = false;              // producer/consumer warp pair per voice group (s2_kernel_pc.cu)
-    int nv = 1;                   // voices per lane: 2 (packed f32x2 arithmetic) for banks wider than a warp
+    uint32_t force_path = 0;      // test hook (S2_FORCE_PATH, see RenderArgs)
     uint32_t* d_stage = nullptr;  // staging for the bulk note-off table when slots are permuted
     // Pipelined mode (s2_bank_set_pipeline): the bank is cut into n_sub contiguous slot ranges, each
     // rendered on its own internal stream.  Consecutive render calls then overlap across sub-banks (no
@@ -217,7 +216,7 @@ uint32_t sub_begin(const s2_bank* b, int k) {
 }
 
 int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t row_stride, float* d_bus_out) {
-    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
+    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices);
     const int p = (int)(b->step % (uint64_t)kMixBufs);
     float* partials = nullptr;
     if (d_bus_out) {
@@ -246,6 +245,8 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
     a.row_stride = row_stride;
     a.bus_partials = partials;
     a.has_sine = b->n_sine ? 1u : 0u;
+    a.one = 1.0f;
+    a.force_path = b->force_path;
     uint32_t* release_row = reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad);
     for (int k = 0; k < b->n_sub; k++) {
         a.slot_begin = sub_begin(b, k);
@@ -262,8 +263,7 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
             CUDA_TRY(cudaEventRecord(b->ev_gather[k][b->table_pending], sk));
         }
         if (d_bus_out && b->step >= (uint64_t)kMixBufs) CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_mix[p], 0));   // partials[p] are free again
-        if (b->pc) CUDA_TRY(s2::launch_render_pc(a, b->filter_kind, sk));
-        else CUDA_TRY(s2::launch_render(a, b->filter_kind, s2::TRACE_NONE, b->nv, sk));
+        CUDA_TRY(s2::launch_render(a, b->filter_kind, s2::TRACE_NONE, sk));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaEventRecord(b->ev_sub[k], sk));
     }
@@ -338,6 +338,8 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     a.row_stride = row_stride;
     a.bus_partials = nullptr;
     a.has_sine = b->n_sine ? 1u : 0u;
+    a.one = 1.0f;
+    a.force_path = b->force_path;
     if (b->ts_main_dirty) {
         // the pre-pass reads the carried phase: order it after whatever the bank's stream wrote
         CUDA_TRY(cudaEventRecord(b->ev_main, b->stream));
@@ -396,7 +398,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     if (b->n_sub > 1 && trace == s2::TRACE_NONE) return bank_render_pipelined(b, frames, d_voice_out, row_stride, d_bus_out);
     if (b->n_sub > 1) { int rc = bank_drain(b); if (rc) return rc; }
 
-    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices, b->nv);
+    const uint32_t n_warps = s2::render_warps((uint32_t)b->n_voices);
     float* partials = nullptr;
     if (d_bus_out) {
         if (n_warps == 1) {
@@ -427,8 +429,9 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     a.row_stride = row_stride;
     a.bus_partials = partials;
     a.has_sine = b->n_sine ? 1u : 0u;
-    if (b->pc && trace == s2::TRACE_NONE) CUDA_TRY(s2::launch_render_pc(a, b->filter_kind, b->stream));
-    else CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->nv, b->stream));
+    a.one = 1.0f;
+    a.force_path = b->force_path;
+    CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
         CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
@@ -514,22 +517,35 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->vpad = (n_voices + 63) & ~(size_t)63;
     b->book.resize(n_voices);
     if (n_voices <= kTsMaxVoices) b->descs.assign(voices, voices + n_voices);
-    b->nv = 1;   // 2 = two voices per lane with packed f32x2 math: fewer issue slots but half the warps; measured no faster
-    b->pc = false;   // measured slower than the one-warp kernel (profiles/r1_notes.md); S2_PC=1 selects it
-    if (const char* f = getenv("S2_PC")) b->pc = f[0] == '1';   // test hook
-    if (const char* f = getenv("S2_FORCE_NV")) {          // test hook: exercise either lane width on any bank
-        if (f[0] == '1') b->nv = 1;
-        if (f[0] == '2') { b->nv = 2; b->pc = false; }
-    }
-    if (filter_kind > S2_FILTER_BIQUAD_LP) { b->nv = 1; b->pc = false; }   // the experimental layouts know two filters
+    if (const char* f = getenv("S2_FORCE_PATH")) b->force_path = (f[0] == '1') ? 1u : (f[0] == '2') ? 2u : 0u;   // test hook
 
     b->voice_of_slot.resize(n_voices);
     b->slot_of_voice.resize(n_voices);
     for (size_t i = 0; i < n_voices; i++) b->voice_of_slot[i] = (uint32_t)i;
     if (n_voices > 32) {
-        auto key = [&](uint32_t v) { return voices[v].active ? voices[v].osc_kind : 4u; };
-        std::stable_sort(b->voice_of_slot.begin(), b->voice_of_slot.end(),
-                         [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+        // (inactive last) x oscillator kind x (does the cutoff / the pitch follow the mod envelope) x when the mod
+        // and the amp envelope come to rest: the 32 voices of a warp then leave the moving-cutoff chunks and the
+        // envelope ramps together instead of waiting for the slowest of a random draw.  Stable: a patch sweep keeps
+        // the variants of one cutoff trajectory next to each other.
+        struct Key { uint32_t kind, follows; float mod_rest, amp_rest; };
+        std::vector<Key> keys(n_voices);
+        for (size_t i = 0; i < n_voices; i++) {
+            const s2_voice_desc& d = voices[i];
+            Key k;
+            k.kind = d.active ? d.osc_kind : 4u;
+            k.follows = d.mod_env_to_osc_freq != 0.0f ? 2u : d.mod_env_to_lpf_freq != 0.0f ? 1u : 0u;
+            k.mod_rest = k.follows ? d.mod_attack_ms + d.mod_decay_ms : 0.0f;
+            k.amp_rest = d.amp_attack_ms + d.amp_decay_ms;
+            keys[i] = k;
+        }
+        std::stable_sort(b->voice_of_slot.begin(), b->voice_of_slot.end(), [&](uint32_t x, uint32_t y) {
+            const Key& a = keys[x];
+            const Key& c = keys[y];
+            if (a.kind != c.kind) return a.kind < c.kind;
+            if (a.follows != c.follows) return a.follows < c.follows;
+            if (a.mod_rest != c.mod_rest) return a.mod_rest < c.mod_rest;
+            return a.amp_rest < c.amp_rest;
+        });
     }
     for (size_t s = 0; s < n_voices; s++) {
         b->slot_of_voice[b->voice_of_slot[s]] = (uint32_t)s;

@@ -1,5 +1,5 @@
 // s2_device.cuh — device-side building blocks shared by the render kernels (s2_kernels.cu: one warp per
-// voice group; s2_kernel_pc.cu: producer/consumer warp pair per voice group).
+// 32 voices; s2_kernel_ts.cu: one warp per voice, lanes = time segments).
 //
 // Arithmetic contract: every operation below that feeds a discrete decision (phase, table index,
 // envelope stage, noise hash) is the reference's binary32 operation, spelled with __f*_rn intrinsics so
@@ -9,6 +9,7 @@
 
 #include "s2_internal.h"
 #include "s2_math.h"
+#include "s2_cutoff.h"
 
 // The biquad's products and sums are rounded separately, as the source reads (dsp_filters.rs:116-128).  A
 // fused (FFMA) form was tried and rejected: a resonant low-cutoff biquad in f32 direct form amplifies
@@ -101,18 +102,24 @@ __device__ __forceinline__ float env_x16(const E& e, float x) {
 // stage's formula bit-for-bit (attack: (1/A)*x + 0; decay: ((S-1)/D)*(x-A) + 1; sustain: 0*x + S; release:
 // ((-S)/R)*(x-Rs) + S; end: 0*x + 0), valid for frame offsets [.., nend).  Offsets below 2^24 only
 // (x = (f32)n exact; nend = first integer whose f32 image reaches the stage boundary).
-struct SegEnv { float es, nex0, ey0; uint32_t nend; };
+struct SegEnv { float es, nex0, ey0; uint32_t nbeg, nend; int stage; };
+
+// first integer frame offset whose f32 image reaches the boundary b (exact below 2^24)
+__device__ __forceinline__ uint32_t env_bound(float b) { return min(__float2uint_ru(b), 1u << 24); }
 
 template <class E>
 __device__ __forceinline__ SegEnv seg_env(const E& e, uint32_t n) {
     const float x = __uint2float_rn(n);
     const int st = env_stage(e, x);
     SegEnv s;
+    s.stage = st;
     s.es = st == 0 ? e.sA : st == 1 ? e.sD : st == 3 ? e.sR : 0.0f;
     s.nex0 = st == 1 ? -e.A : st == 3 ? -e.Rs : -0.0f;             // x + (-0.0) == x
     s.ey0 = st == 1 ? 1.0f : (st == 2 || st == 3) ? e.S : 0.0f;
     const float b = st == 0 ? e.A : st == 1 ? e.AD : st == 2 ? e.Rs : st == 3 ? e.E : 4.0e9f;
-    s.nend = min(__float2uint_ru(b), 1u << 24);
+    const float a = st == 0 ? 0.0f : st == 1 ? e.A : st == 2 ? e.AD : st == 3 ? e.Rs : e.E;
+    s.nend = env_bound(b);
+    s.nbeg = env_bound(a);
     return s;
 }
 __device__ __forceinline__ float seg_eval(const SegEnv& s, float x) {
@@ -178,24 +185,17 @@ __device__ __forceinline__ void make_osc(OscC& o, float fo, float sr) {
 // FILTER template values = S2_FILTER_* of include/s2_cuda.h
 enum { FILT_ONE_POLE = 0, FILT_BIQUAD_LP = 1, FILT_BIQUAD_HP = 2, FILT_BIQUAD_BP = 3, FILT_FIRST_LP = 4, FILT_FIRST_HP = 5 };
 
-template <int FILTER>
-__device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float sr) {
-    c.fl_bits = __float_as_uint(fl);
+// theta = (2 pi f) / sr: try3/filters.rs:21 with the sign dropped, dsp_filters.rs:107
+__device__ __forceinline__ float theta_ref(float fl, float sr) {
     const float pi = 3.14159274101257324219f;
-    if (FILTER == 0) {
-        // try3/filters.rs:21: (-2.0 * pi * freq / sample_rate).exp()
-        float t = __fmul_rn(-2.0f, pi);
-        t = __fmul_rn(t, fl);
-        t = __fdiv_rn(t, sr);
-        const float k = exp_ref(t);
-        c.c0 = k;
-        c.c1 = __fsub_rn(1.0f, k);
-        c.c2 = 0.0f;
-    } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
+    return __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, pi), fl), sr);
+}
+
+// Coefficients of every filter but the one-pole from theta, all transcendentals in binary64 rounded once
+template <int FILTER>
+__device__ __forceinline__ void make_filt_theta(FiltC& c, float th, float damp) {
+    if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
         // try3/dsp_filters.rs:99-109 (low-pass), :149-159 (high-pass: alpha = (1/2 + beta + gamma) / 4)
-        float th = __fmul_rn(2.0f, pi);
-        th = __fmul_rn(th, fl);
-        th = __fdiv_rn(th, sr);
         float s, co;
         s2_sincosf(th, &s, &co);
         const float hd = __fmul_rn(damp, 0.5f);                      // damp / 2.0: scaling by a power of two, same bits
@@ -212,9 +212,6 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         c.c2 = __fmul_rn(2.0f, gamma);
     } else if (FILTER == FILT_BIQUAD_BP) {
         // try3/dsp_filters.rs:197-207; `damp` carries the quality factor
-        float th = __fmul_rn(2.0f, pi);
-        th = __fmul_rn(th, fl);
-        th = __fdiv_rn(th, sr);
         const float tn = s2_tanf(__fdiv_rn(th, __fmul_rn(2.0f, damp)));
         const float beta = __fmul_rn(0.5f, __fdiv_rn(__fsub_rn(1.0f, tn), __fadd_rn(1.0f, tn)));
         float s, co;
@@ -226,9 +223,6 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         c.c2 = __fmul_rn(2.0f, gamma);
     } else {
         // try3/dsp_filters.rs:30-32 (first-order low-pass) / :64-66 (high-pass): c0 = alpha, c2 = gamma
-        float th = __fmul_rn(2.0f, pi);
-        th = __fmul_rn(th, fl);
-        th = __fdiv_rn(th, sr);
         float s, co;
         s2_sincosf(th, &s, &co);
         const float gamma = __fdiv_rn(co, __fadd_rn(1.0f, s));
@@ -238,29 +232,113 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
     }
 }
 
+// Coefficients of a RESTING cutoff (every frame whose mod envelope is in sustain / end, or whose cutoff does not
+// follow it; also the scalar tail): the reference's chain, transcendentals in binary64.
+template <int FILTER>
+__device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float sr) {
+    c.fl_bits = __float_as_uint(fl);
+    if (FILTER == 0) {
+        // try3/filters.rs:21: (-2.0 * pi * freq / sample_rate).exp()
+        const float pi = 3.14159274101257324219f;
+        float t = __fmul_rn(-2.0f, pi);
+        t = __fmul_rn(t, fl);
+        t = __fdiv_rn(t, sr);
+        const float k = exp_ref(t);
+        c.c0 = k;
+        c.c1 = __fsub_rn(1.0f, k);
+        c.c2 = 0.0f;
+    } else {
+        make_filt_theta<FILTER>(c, theta_ref(fl, sr), damp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MOVING cutoff (s2_cutoff.h): the mod envelope is in a ramp (attack / decay / release) and the cutoff follows it.
+
+struct CutP {            // per-voice constants of the moving evaluation
+    float theta0;        // (2 pi cutoff) / sr
+    float amt;           // mod_env_to_lpf_freq
+    float damp, hd;      // damping, damping / 2
+};
+__device__ __forceinline__ CutP make_cutp(float lpf, float amt_lpf, float damp, float sr) {
+    CutP c;
+    c.theta0 = theta_ref(lpf, sr);
+    c.amt = amt_lpf;
+    c.damp = damp;
+    c.hd = __fmul_rn(damp, 0.5f);
+    return c;
+}
+
+// The window of frame offset n inside mod-envelope segment sm (a ramp).  Valid iff the 32 frames of the window
+// lie in the segment, the centre angle leaves room below pi, the sweep across half a window stays within
+// 2^-7 (theta changes by the factor 2^(amt * es) per frame: |d| <= thc * 16 ln 2 |amt es| (1 + ...) < thc * 12 |amt es|)
+// and the damping suits the straight-line division.  A pure function of (voice, n >> 5).
+template <int FILTER>
+__device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
+    const uint32_t k = n >> s2c::kWinShift;
+    W.k = k;
+    const uint32_t w0 = k << s2c::kWinShift;
+    const float xc = __uint2float_rn(w0 + 16u);
+    const float thc = s2c::theta_at<float>(seg_eval(sm, xc), cp.amt, cp.theta0);
+    const float r12 = __fmul_rn(fabsf(__fmul_rn(cp.amt, sm.es)), 12.0f);
+    bool valid = w0 >= sm.nbeg && w0 + 32u <= sm.nend && thc <= s2c::kThetaMax && r12 < 0.5f &&
+                 __fmul_rn(thc, r12) <= s2c::kWinDelta;
+    if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) valid = valid && cp.hd >= 0.0f && cp.hd <= 8.0f;
+    if (FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_BP) valid = false;      // these never look at a window
+    W.valid = valid ? 1u : 0u;
+    W.thc = thc;
+    if (valid) {
+        double sd, cd;
+        s2_sincos_d((double)thc, &sd, &cd);
+        s2c::split_hi_lo(sd, &W.Ah, &W.Al);
+        s2c::split_hi_lo(cd, &W.Bh, &W.Bl);
+    } else {
+        W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    }
+}
+
+// Coefficients of one moving frame (scalar form): m = the mod envelope at frame n (inside segment sm).
+template <int FILTER>
+__device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const SegEnv& sm, const CutP& cp, float one,
+                                             uint32_t n, float m) {
+    const float th = s2c::theta_at<float>(m, cp.amt, cp.theta0);
+    c.fl_bits = kNoKey;                                   // not a memo of any resting cutoff
+    if (FILTER == FILT_ONE_POLE) {
+        const float k = s2c::exp_neg_fast<float>(th);
+        c.c0 = k;
+        c.c1 = __fsub_rn(1.0f, k);
+        c.c2 = 0.0f;
+        return;
+    }
+    if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, th, cp.damp); return; }
+    if ((n >> s2c::kWinShift) != W.k) make_window<FILTER>(W, sm, cp, n);
+    if (W.valid) {
+        float s, co;
+        s2c::window_sincos<float>(W, th, &s, &co);
+        if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
+            s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
+        } else {
+            const float gamma = __fdiv_rn(co, __fadd_rn(1.0f, s));
+            c.c0 = __fmul_rn(FILTER == FILT_FIRST_LP ? __fsub_rn(1.0f, gamma) : __fadd_rn(1.0f, gamma), 0.5f);
+            c.c1 = 0.0f;
+            c.c2 = gamma;
+        }
+    } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
+        float s, co;
+        s2_sincosf(th, &s, &co);
+        s2c::biquad_lp_hp_any<FILTER == FILT_BIQUAD_HP>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
+    } else {
+        make_filt_theta<FILTER>(c, th, cp.damp);
+    }
+}
+
+// Does the cutoff of a voice move at x16 frame n?  (amount != 0 and the mod envelope is in a ramp)
+__device__ __forceinline__ bool stage_moves(int stage) { return stage == 0 || stage == 1 || stage == 3; }
+
 // The compact envelope the classifier and the per-frame evaluation need (env_stage / env_x16); the
 // scalar-tail envelope (env_scalar) needs the full EnvP.
 struct EnvQ { float A, AD, S, Rs, E, sA, sD, sR; };
 __device__ __forceinline__ EnvQ compact(const EnvP& e) { return {e.A, e.AD, e.S, e.Rs, e.E, e.sA, e.sD, e.sR}; }
-
-// Decode one voice's parameter column (struct-of-arrays, see s2_internal.h).
-__device__ __forceinline__ Lane load_lane(const float* __restrict__ P, uint32_t vp, float sr) {
-    Lane L;
-    L.kind = __float_as_uint(P[P_KIND * vp]);
-    const uint32_t seed = __float_as_uint(P[P_SEED * vp]);
-    L.rot = (seed << 5) | (seed >> 27);
-    L.pitch = P[P_PITCH * vp];
-    L.gain = P[P_GAIN * vp];
-    L.namt = P[P_NOISE * vp];
-    L.lpf = P[P_LPF * vp];
-    L.damp = P[P_DAMP * vp];
-    L.amt_osc = P[P_AMT_OSC * vp];
-    L.amt_lpf = P[P_AMT_LPF * vp];
-    const uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
-    make_env(L.amp, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
-    make_env(L.mod, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
-    return L;
-}
 
 // ------------------------------------------------------------------------------------------
 // One frame of one voice.
@@ -298,13 +376,16 @@ __device__ __forceinline__ float osc_step(uint32_t kind, const OscC& o, float& p
     return y;
 }
 
-// try3/hashnoise.rs:33-68.  value / 65535 is replaced by fma(v, hi, v*lo) with hi + lo = 1/65535
-// to 48 bits: equal to the IEEE quotient for all 65,536 possible values (tests/test_host_logic.py).
+// try3/hashnoise.rs:33-68.  value / 65535 is replaced by fma(v, 0x1.0001p-16, 2^-45): v * 0x1.0001p-16 is exact in
+// the fma and lies below the true quotient by less than 2^-32, with no rounding boundary in between except
+// when it sits on one itself (a tie), which the tiny addend resolves upwards as the true quotient would be:
+// equal to the IEEE quotient for all 65,536 possible values (tests/test_oracle_kats.py).
 // (q * 2) - 1 is one fma because q * 2 is exact.
+constexpr float kNoiseHi = 0x1.0001p-16f, kNoiseEps = 0x1p-45f;
 __device__ __forceinline__ float noise_fast(uint32_t rot, uint32_t n) {
     const uint32_t h = (rot ^ n) * 0x9e3779b9u;
     const float v = __uint2float_rn(h & 0xffffu);
-    const float q = __fmaf_rn(v, 0x1.0001p-16f, __fmul_rn(v, 0x1.0001p-48f));
+    const float q = __fmaf_rn(v, kNoiseHi, kNoiseEps);
     return __fmaf_rn(q, 2.0f, -1.0f);
 }
 
@@ -344,223 +425,157 @@ __device__ __forceinline__ float filt_step(float u, const FiltC& c, FiltS& s) {
     }
 }
 
+// Two frames of the filter, u2 = inputs of frames (i, i + 1), with per-frame coefficients ca / cb (the same
+// object twice on the fast path).  Same operations as filt_step twice; the feed-forward product c0 * sx of the
+// second-order filters is computed for both frames in one packed multiply (it feeds scalar adds only: no
+// contraction, see the hazard note below).
+template <int FILTER>
+__device__ __forceinline__ float2 filt_step2(float2 u2, const FiltC& ca, const FiltC& cb, FiltS& s) {
+    if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP || FILTER == FILT_BIQUAD_BP) {
+        float sxa, sxb;
+        if (FILTER == FILT_BIQUAD_LP) {
+            sxa = __fadd_rn(__fmaf_rn(2.0f, s.x1, u2.x), s.x2);
+            sxb = __fadd_rn(__fmaf_rn(2.0f, u2.x, u2.y), s.x1);
+        } else if (FILTER == FILT_BIQUAD_HP) {
+            sxa = __fadd_rn(__fmaf_rn(-2.0f, s.x1, u2.x), s.x2);
+            sxb = __fadd_rn(__fmaf_rn(-2.0f, u2.x, u2.y), s.x1);
+        } else {
+            sxa = __fsub_rn(u2.x, s.x2);
+            sxb = __fsub_rn(u2.y, s.x1);
+        }
+        const float2 p = s2c::vmul(make_float2(ca.c0, cb.c0), make_float2(sxa, sxb));
+        float ta = __fadd_rn(p.x, __fmul_rn(ca.c2, s.y1));
+        ta = __fsub_rn(ta, __fmul_rn(ca.c1, s.y2));
+        float tb = __fadd_rn(p.y, __fmul_rn(cb.c2, ta));
+        tb = __fsub_rn(tb, __fmul_rn(cb.c1, s.y1));
+        s.x2 = u2.x; s.x1 = u2.y; s.y2 = ta; s.y1 = tb;
+        return make_float2(ta, tb);
+    } else {
+        const float ya = filt_step<FILTER>(u2.x, ca, s);
+        const float yb = filt_step<FILTER>(u2.y, cb, s);
+        return make_float2(ya, yb);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// Lane-vector arithmetic.  A lane carries NV voices (NV = 1: one voice, scalar FP32 instructions;
-// NV = 2: two voices packed in a float2 and computed with Blackwell's packed-FP32 instructions
-// FADD2 / FMUL2 / FFMA2, which retire two IEEE-754 round-to-nearest results per issue slot — the
-// render loop is issue-bound, not FLOP-bound: profiles/r1_notes.md).  Each element is rounded
-// exactly like the scalar instruction, so parity is unchanged.
-
-template <int NV> struct VT;
-template <> struct VT<1> { using type = float; };
-template <> struct VT<2> { using type = float2; };
-template <int NV> using vf = typename VT<NV>::type;
-
-__device__ __forceinline__ float vget(float v, int) { return v; }
-__device__ __forceinline__ float vget(float2 v, int e) { return e ? v.y : v.x; }
-__device__ __forceinline__ void vset(float& v, int, float x) { v = x; }
-__device__ __forceinline__ void vset(float2& v, int e, float x) { if (e) v.y = x; else v.x = x; }
-template <int NV> __device__ __forceinline__ vf<NV> vsplat(float x);
-template <> __device__ __forceinline__ float vsplat<1>(float x) { return x; }
-template <> __device__ __forceinline__ float2 vsplat<2>(float x) { return make_float2(x, x); }
-
+// Packed arithmetic: Blackwell's FADD2 / FMUL2 / FFMA2 retire two IEEE-754 round-to-nearest results per issue
+// slot — the render loop is issue-bound, not FLOP-bound (profiles/r1_notes.md).  Each element is rounded exactly
+// like the scalar instruction, so parity is unchanged.
+//
 // CONTRACTION HAZARD (ptxas 12.9, sm_100a): a packed multiply whose result feeds a packed add is fused
 // into FFMA2 — with the __fmul2_rn/__fadd2_rn builtins AND with explicit `mul.rn.f32x2` / `add.rn.f32x2`
 // PTX, -fmad=false notwithstanding (tools/ubench/fuse_check.cu; scalar __fmul_rn + __fadd_rn is not
 // fused).  That moves results by an ulp and can flip a square wave's sign.  Rule used in this file: the
-// result of pmul2 never feeds padd2; where the reference adds to a product, the add is done with scalar
-// __fadd_rn per element (vadd(float2, float2) below always is).
-__device__ __forceinline__ float2 padd2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 pmul2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 pfma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
+// result of pmul2 never feeds padd2; where the reference adds to a rounded product, the add is either scalar
+// __fadd_rn per element or s2c::vaddp (an fma with a multiplicand of 1 that ptxas cannot see through).
+__device__ __forceinline__ float2 padd2(float2 a, float2 b) { return s2c::vadd(a, b); }
+__device__ __forceinline__ float2 pmul2(float2 a, float2 b) { return s2c::vmul(a, b); }
+__device__ __forceinline__ float2 pfma2(float2 a, float2 b, float2 c) { return s2c::vfma(a, b, c); }
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
 
-__device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return pmul2(a, b); }
-__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return pfma2(a, b, c); }
-
-// Per-lane constants and state of the fast path, NV voices wide.
-template <int NV> struct FastV {
+// Per-lane constants and state of the fast paths (registers).
+struct FastV {
     // oscillator (derived from the period; negations are stored so the loop only adds)
-    vf<NV> P, d, slope, nhalf, ts1, ts2;
+    float P, d, slope, nhalf, ts1, ts2;
     // patch
-    vf<NV> gain, namt;
-    // filter: one-pole c0 = k, c1 = 1 - k; biquad c0 = 2*alpha, nc1 = -2*beta, c2 = 2*gamma
-    vf<NV> c0, c1, c2;
-    // envelope segment g = es * (x + nex0) + ey0
-    vf<NV> es, nex0, ey0;
+    float gain, namt;
+    // filter of a resting cutoff: one-pole c0 = k, c1 = 1 - k; second order c0 = 2*alpha, c1 = 2*beta, c2 = 2*gamma
+    float c0, c1, c2;
+    // amp envelope segment of the lane's current frame: g = es * (x + nex0) + ey0 for frame offsets [.., seg_end)
+    float es, nex0, ey0;
+    uint32_t seg_end;
     // carried state
-    vf<NV> ph, x1, x2, y1, y2;
+    float ph, x1, x2, y1, y2;
 };
 
-struct FastEnv { float es, ex0, ey0; };   // g = es * (x - ex0) + ey0 reproduces each stage bit-exactly
+// How a chunk evaluates the amp envelope.
+enum { G_CONST = 0,      // every frame of the chunk lies in a segment of slope 0 (sustain, end): g = ey0
+       G_LINE = 1,       // every frame lies in the lane's current segment: one line, two frames per instruction
+       G_ANY = 2 };      // a stage boundary falls inside the chunk for some lane: per pair, the full stage chain at boundaries
 
-// Fast chunk: period, cutoff and envelope segment are constant over the 32 frames of every voice
-// of the warp.  KIND >= 0: every voice of the warp runs that oscillator (banks are sorted by kind).
-template <int NV, int FILTER, int KIND, bool GCONST, bool NAMT0, int TRACE>
-__device__ __forceinline__ void chunk_fast(FastV<NV>& F, const uint32_t (&kind)[NV], const uint32_t (&rot)[NV],
-                                           const uint32_t (&n0)[NV], float* __restrict__ tile, int lane,
-                                           const float* sintab) {
-    const vf<NV> one = vsplat<NV>(1.0f), none = vsplat<NV>(-1.0f), two = vsplat<NV>(2.0f);
-    uint32_t n[NV];
-    vf<NV> xf;
+// Waveform of frames (i, i + 1) from their phases, period constant (the `% period` is a no-op, see osc_step).
+template <int KIND>
+__device__ __forceinline__ float2 wave2(const FastV& F, float2 ph2, float hbig, uint32_t kind, const float* sintab) {
+    const float2 x2 = pmul2(splat2(F.P), ph2);                 // period.mul_add(phase, 0)
+    float2 osc2;
+    if (KIND == 1) {
+        osc2 = pfma2(splat2(F.slope), x2, splat2(1.0f));
+    } else if (KIND == 0) {
+        // x < P/2 ? +1 : -1 without a compare or bit surgery: s = sat(2^60 * (P/2 - x)) is exactly 1 when
+        // x < P/2 and exactly 0 otherwise (the fma is exact in sign; two distinct binary32 values of this
+        // magnitude differ by >= 2^-24, so the product is >= 2^36 before the clamp; equality gives +0; a
+        // NaN clamps to 0, i.e. -1, as `NaN < h` is false), and 2 s - 1 is exact.
+        const float2 sq = make_float2(__saturatef(__fmaf_rn(x2.x, -0x1p60f, hbig)),
+                                      __saturatef(__fmaf_rn(x2.y, -0x1p60f, hbig)));
+        osc2 = pfma2(sq, splat2(2.0f), splat2(-1.0f));
+    } else if (KIND == 2) {
+        const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
+        const float2 a = pfma2(splat2(F.ts1), x2, splat2(1.0f));
+        const float2 b = pfma2(splat2(F.ts2), dl, splat2(-1.0f));
+        osc2.x = dl.x < 0.0f ? a.x : b.x;
+        osc2.y = dl.y < 0.0f ? a.y : b.y;
+    } else {
 #pragma unroll
-    for (int e = 0; e < NV; e++) { n[e] = n0[e]; vset(xf, e, __uint2float_rn(n0[e])); }   // exact: n0 + 32 <= 2^24
-    // 8 frames per trip: long enough for the scheduler to overlap neighbouring frames, short enough to
-    // live in the instruction cache.
-#pragma unroll 2
-    for (int j = 0; j < kChunk / 4; j++) {
-        float o4[NV][4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const vf<NV> ph0 = F.ph;
-            // ---- oscillator: x = period.mul_add(phase, 0); `% period` is a no-op (see osc_step)
-            const vf<NV> x = vmul(F.P, ph0);
-            vf<NV> osc;
-            if (KIND == 1) {                                       // Saw: fma(-2/P, x, 1)
-                osc = vfma(F.slope, x, one);
-            } else if (KIND == 0) {                                // Square: x < P/2 ? 1 : -1
-                // sign(x - half) picks +-1: (x - half) is -0 never, +0 when equal -> -1 like `<`
-                const vf<NV> dl = vadd(x, F.nhalf);
-#pragma unroll
-                for (int e = 0; e < NV; e++)
-                    vset(osc, e, __uint_as_float((__float_as_uint(vget(dl, e)) & 0x80000000u) ^ 0xbf800000u));
-            } else if (KIND == 2) {                                // Triangle
-                const vf<NV> dl = vadd(x, F.nhalf);
-                const vf<NV> a = vfma(F.ts1, x, one);
-                const vf<NV> b = vfma(F.ts2, dl, none);
-#pragma unroll
-                for (int e = 0; e < NV; e++) vset(osc, e, vget(dl, e) < 0.0f ? vget(a, e) : vget(b, e));
-            } else {                                               // Sine, or a warp of mixed kinds
-#pragma unroll
-                for (int e = 0; e < NV; e++) {
-                    const uint32_t k = KIND == 3 ? 3u : kind[e];
-                    const float xe = vget(x, e), Pe = vget(F.P, e), he = -vget(F.nhalf, e);
-                    float y;
-                    if (k == 1u) y = __fmaf_rn(vget(F.slope, e), xe, 1.0f);
-                    else if (k == 0u) y = xe < he ? 1.0f : -1.0f;
-                    else if (k == 2u) {
-                        const float a = __fmaf_rn(vget(F.ts1, e), xe, 1.0f);
-                        const float b = __fmaf_rn(vget(F.ts2, e), __fsub_rn(xe, he), -1.0f);
-                        y = xe < he ? a : b;
-                    } else {                                       // try3/lookup.rs:46-85 on SIN_TABLE
-                        const float tv = __fdiv_rn(__fmul_rn(xe, 1024.0f), Pe);
-                        const uint32_t i1 = __float2uint_rz(tv);
-                        const uint32_t i2 = (i1 + 1u) & 1023u;
-                        const float s1 = i1 < 1024u ? sintab[i1] : 0.0f;
-                        const float s2 = sintab[i2];
-                        y = __fmaf_rn(__fsub_rn(s2, s1), __fsub_rn(tv, __uint2float_rn(i1)), s1);
-                    }
-                    vset(osc, e, y);
-                }
+        for (int e = 0; e < 2; e++) {
+            const uint32_t k = KIND == 3 ? 3u : kind;
+            const float xe = e ? x2.y : x2.x, he = -F.nhalf;
+            float y;
+            if (k == 1u) y = __fmaf_rn(F.slope, xe, 1.0f);
+            else if (k == 0u) y = xe < he ? 1.0f : -1.0f;
+            else if (k == 2u) {
+                const float a = __fmaf_rn(F.ts1, xe, 1.0f);
+                const float b = __fmaf_rn(F.ts2, __fsub_rn(xe, he), -1.0f);
+                y = xe < he ? a : b;
+            } else {                                       // try3/lookup.rs:46-85 on SIN_TABLE
+                const float tv = __fdiv_rn(__fmul_rn(xe, 1024.0f), F.P);
+                const uint32_t i1 = __float2uint_rz(tv);
+                const uint32_t i2 = (i1 + 1u) & 1023u;
+                const float s1 = i1 < 1024u ? sintab[i1] : 0.0f;
+                const float s2 = sintab[i2];
+                y = __fmaf_rn(__fsub_rn(s2, s1), __fsub_rn(tv, __uint2float_rn(i1)), s1);
             }
-            // ---- phase step: t = phase + 1/P; `% 1.0` == subtract 1 when t >= 1 (t < 2, exact)
-            const vf<NV> t = vadd(ph0, F.d);
-            vf<NV> w;
-#pragma unroll
-            for (int e = 0; e < NV; e++) vset(w, e, vget(t, e) >= 1.0f ? 1.0f : 0.0f);
-            F.ph = vfma(w, none, t);                               // t - w, exact product
-            // ---- noise (try3/hashnoise.rs:33-68): integer hash, then v/65535*2-1 (see noise_fast)
-            vf<NV> v;
-#pragma unroll
-            for (int e = 0; e < NV; e++) {
-                const uint32_t h = (rot[e] ^ n[e]) * 0x9e3779b9u;
-                vset(v, e, __uint2float_rn(h & 0xffffu));
-                n[e] += 1u;
-            }
-            const vf<NV> q = vfma(v, vsplat<NV>(0x1.0001p-16f), vmul(v, vsplat<NV>(0x1.0001p-48f)));
-            const vf<NV> nz = vfma(q, two, none);
-            // ---- process.rs:341-358: gain and noise amount are ADDED on the x16 path.
-            // nz + 0.0 == nz bit-for-bit (nz is never -0.0), so NAMT0 drops that add.
-            const vf<NV> u = vadd(vadd(osc, F.gain), NAMT0 ? nz : vadd(nz, F.namt));
-            // ---- filter
-            vf<NV> y;
-            if (FILTER == 0) {
-                // try3/filters.rs:23-33: a0.mul_add(input, k * last)
-                y = vfma(F.c1, u, vmul(F.c0, F.y1));
-                F.y1 = y;
-            } else {
-                // try3/dsp_filters.rs:116-128 (see filt_step): 2*(alpha*(x + 2*x1 + x2) + gamma*y1 - beta*y2)
-                vf<NV> sx = vfma(two, F.x1, u);
-                sx = vadd(sx, F.x2);
-                vf<NV> tt = vmul(F.c0, sx);
-                tt = vadd(tt, vmul(F.c2, F.y1));
-                y = vadd(tt, vmul(F.c1, F.y2));                             // c1 holds -2*beta: exact negation
-                F.x2 = F.x1; F.x1 = u; F.y2 = F.y1; F.y1 = y;
-            }
-            // ---- amp envelope (old/simdtest.rs:270-330 on one segment) and gain (process.rs:373-378)
-            vf<NV> g;
-            if (GCONST) g = F.ey0;
-            else {
-                g = vadd(vmul(F.es, vadd(xf, F.nex0)), F.ey0);
-                xf = vadd(xf, one);
-            }
-            const vf<NV> out = TRACE == TRACE_PHASE ? ph0 : vmul(y, g);
-#pragma unroll
-            for (int e = 0; e < NV; e++) o4[e][i] = vget(out, e);
+            if (e) osc2.y = y; else osc2.x = y;
         }
-#pragma unroll
-        for (int e = 0; e < NV; e++)
-            *reinterpret_cast<float4*>(tile + (e * 32 + lane) * kTileStride + 4 * j) =
-                make_float4(o4[e][0], o4[e][1], o4[e][2], o4[e][3]);
     }
+    return osc2;
 }
 
-// Time-packed fast chunk for one voice per lane: the render loop is issue-bound, not FLOP-bound
-// (profiles/r1_notes.md), and FADD2/FMUL2/FFMA2 retire two IEEE-754 results per issue slot.  The two
-// recurrences (phase, filter) stay scalar — a packed op has twice the latency — while everything that
-// is feed-forward (waveform, noise map, gain/noise combine, envelope, output gain) is computed for
-// frames (i, i+1) of the voice in one packed instruction.  Element-wise rounding is identical.
-// ALIGNED8: the voice's frame offset and its rotated seed are multiples of 8 (seeds below 2^27 rotate to multiples
-// of 32), so (seed' ^ (offset + i)) == (seed' ^ offset) + i and the hash of frame i is one add with an immediate.
-// GCONST = false: the amp envelope is evaluated per frame with its full stage chain (env_x16), so
-// attack / decay / release ramps and their boundaries stay on the fast path.
-template <int FILTER, int KIND, bool GCONST, bool NAMT0, bool ALIGNED8, int TRACE>
-__device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restrict__ amp, uint32_t kind, uint32_t rot,
+// Noise of two frames from their hash words, and the filter input u = (osc + gain) + (noise + amount)
+// (process.rs:341-358: gain and amount are ADDED on the x16 path; nz + 0.0 == nz bit-for-bit, so NAMT0 drops it)
+template <bool NAMT0>
+__device__ __forceinline__ float2 input2(const FastV& F, float2 osc2, uint32_t ha, uint32_t hb) {
+    const float2 v2 = make_float2(__uint2float_rn(ha & 0xffffu), __uint2float_rn(hb & 0xffffu));
+    const float2 q2 = pfma2(v2, splat2(kNoiseHi), splat2(kNoiseEps));
+    const float2 nz2 = pfma2(q2, splat2(2.0f), splat2(-1.0f));
+    return padd2(padd2(osc2, splat2(F.gain)), NAMT0 ? nz2 : padd2(nz2, splat2(F.namt)));
+}
+
+// Time-packed fast chunk: 32 frames of one voice per lane with period, cutoff and (G_CONST / G_LINE) amp-envelope
+// segment constant.  The two recurrences (phase, filter) stay scalar — a packed op has twice the latency — while
+// everything that is feed-forward (waveform, noise map, gain / noise combine, envelope, output gain, the filter's
+// input product) is computed for frames (i, i + 1) of the voice in one packed instruction.  Element-wise rounding
+// is identical to the scalar form.
+// FASTHASH: the noise amount is +0.0 and the voice's frame offset and rotated seed are multiples of 8 (seeds below
+// 2^27 rotate to multiples of 32), so (seed' ^ (offset + i)) == (seed' ^ offset) + i and the hash of frame i is one
+// add with an immediate.
+template <int FILTER, int KIND, int GMODE, bool FASTHASH, int TRACE>
+__device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvP* __restrict__ amp, float one, uint32_t kind, uint32_t rot,
                                               uint32_t n0, float* __restrict__ row, const float* sintab) {
-    const float2 one2 = make_float2(1.0f, 1.0f), none2 = make_float2(-1.0f, -1.0f), two2 = make_float2(2.0f, 2.0f);
-    const float2 P2 = make_float2(F.P, F.P), slope2 = make_float2(F.slope, F.slope);
-    const float2 ts1_2 = make_float2(F.ts1, F.ts1), ts2_2 = make_float2(F.ts2, F.ts2);
-    const float2 gain2 = make_float2(F.gain, F.gain), namt2 = make_float2(F.namt, F.namt);
-    const float2 ey0_2 = make_float2(F.ey0, F.ey0);
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);               // (P / 2) * 2^60, exact
     uint32_t n = n0;
-    float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
-    EnvP A;
-    SegEnv sg = {0.0f, 0.0f, 0.0f, 0u};
-    uint32_t ne = n0;                                             // frame offset of the next envelope pair
-    if (!GCONST) { A = *amp; sg = seg_env(A, n0); }
+    float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));       // exact: n0 + 32 <= 2^24
+    SegEnv sg = {0.0f, 0.0f, 0.0f, 0u, 0u, 0};
+    if (GMODE == G_ANY) sg = seg_env(*amp, n0);
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
-    fc.c0 = F.c0; fc.c1 = FILTER == 0 ? F.c1 : -F.c1; fc.c2 = F.c2; fc.fl_bits = 0;   // F.c1 holds -2*beta for the biquad
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
     float ph = F.ph;
     // 8 frames per trip: long enough to overlap neighbouring frames, short enough for the instruction cache
 #pragma unroll 1
     for (int jt = 0; jt < kChunk / S2_TRIP; jt++) {
-    const uint32_t nb = rot ^ n;                                  // hash input base of this trip
-    // ALIGNED8 (offset and rot both multiples of 8): nb ^ i == nb + i for i < 8, so the hash of frame i is
-    // nb * C + i * C: one multiply per trip and one add with an immediate per frame
-    const uint32_t nbc = nb * 0x9e3779b9u;
+    // FASTHASH: nb ^ i == nb + i for i < 8, so the hash of frame i is nb * C + i * C: one multiply per trip and
+    // one add with an immediate per frame
+    const uint32_t nbc = (rot ^ n) * 0x9e3779b9u;
 #pragma unroll
     for (int jj = 0; jj < S2_TRIP / 4; jj++) {
         const int j = (S2_TRIP / 4) * jt + jj;
@@ -569,85 +584,39 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
         for (int h = 0; h < 2; h++) {
             // ---- phase recurrence, two frames (try3/oscillators.rs:377-381; see osc_step)
             const float pa = ph;
-            const float ta = __fadd_rn(pa, F.d);
-            const float pb = wrap_unit(ta);
-            const float tb = __fadd_rn(pb, F.d);
-            ph = wrap_unit(tb);
+            const float pb = wrap_unit(__fadd_rn(pa, F.d));
+            ph = wrap_unit(__fadd_rn(pb, F.d));
             const float2 ph2 = make_float2(pa, pb);
-            // ---- waveform: x = period.mul_add(phase, 0); `% period` is a no-op
-            const float2 x2 = pmul2(P2, ph2);
-            float2 osc2;
-            if (KIND == 1) {
-                osc2 = pfma2(slope2, x2, one2);
-            } else if (KIND == 0) {
-                // x < P/2 ? +1 : -1 without a compare or bit surgery: s = sat(2^60 * (P/2 - x)) is exactly 1 when
-                // x < P/2 and exactly 0 otherwise (the fma is exact in sign; two distinct binary32 values of this
-                // magnitude differ by >= 2^-24, so the product is >= 2^36 before the clamp; equality gives +0; a
-                // NaN clamps to 0, i.e. -1, as `NaN < h` is false), and 2 s - 1 is exact.
-                const float2 sq = make_float2(__saturatef(__fmaf_rn(x2.x, -0x1p60f, hbig)),
-                                              __saturatef(__fmaf_rn(x2.y, -0x1p60f, hbig)));
-                osc2 = pfma2(sq, two2, none2);
-            } else if (KIND == 2) {
-                const float2 dl = make_float2(__fadd_rn(x2.x, F.nhalf), __fadd_rn(x2.y, F.nhalf));
-                const float2 a = pfma2(ts1_2, x2, one2);
-                const float2 b = pfma2(ts2_2, dl, none2);
-                osc2.x = dl.x < 0.0f ? a.x : b.x;
-                osc2.y = dl.y < 0.0f ? a.y : b.y;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const uint32_t k = KIND == 3 ? 3u : kind;
-                    const float xe = e ? x2.y : x2.x, he = -F.nhalf;
-                    float y;
-                    if (k == 1u) y = __fmaf_rn(F.slope, xe, 1.0f);
-                    else if (k == 0u) y = xe < he ? 1.0f : -1.0f;
-                    else if (k == 2u) {
-                        const float a = __fmaf_rn(F.ts1, xe, 1.0f);
-                        const float b = __fmaf_rn(F.ts2, __fsub_rn(xe, he), -1.0f);
-                        y = xe < he ? a : b;
-                    } else {                                       // try3/lookup.rs:46-85 on SIN_TABLE
-                        const float tv = __fdiv_rn(__fmul_rn(xe, 1024.0f), F.P);
-                        const uint32_t i1 = __float2uint_rz(tv);
-                        const uint32_t i2 = (i1 + 1u) & 1023u;
-                        const float s1 = i1 < 1024u ? sintab[i1] : 0.0f;
-                        const float s2 = sintab[i2];
-                        y = __fmaf_rn(__fsub_rn(s2, s1), __fsub_rn(tv, __uint2float_rn(i1)), s1);
-                    }
-                    if (e) osc2.y = y; else osc2.x = y;
-                }
-            }
+            const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
             // ---- noise (try3/hashnoise.rs:33-68)
             const uint32_t fi = 4u * jj + 2u * h;                 // frame index inside the trip (compile-time)
-            const uint32_t ha = ALIGNED8 ? nbc + fi * 0x9e3779b9u : (rot ^ (n + fi)) * 0x9e3779b9u;
-            const uint32_t hb = ALIGNED8 ? nbc + (fi + 1u) * 0x9e3779b9u : (rot ^ (n + fi + 1u)) * 0x9e3779b9u;
-            const float2 v2 = make_float2(__uint2float_rn(ha & 0xffffu), __uint2float_rn(hb & 0xffffu));
-            const float2 q2 = pfma2(v2, make_float2(0x1.0001p-16f, 0x1.0001p-16f),
-                                         pmul2(v2, make_float2(0x1.0001p-48f, 0x1.0001p-48f)));
-            const float2 nz2 = pfma2(q2, two2, none2);
-            // ---- process.rs:341-358 (ADD, x16 quirk); nz + 0.0 == nz bit-for-bit
-            const float2 u2 = padd2(padd2(osc2, gain2), NAMT0 ? nz2 : padd2(nz2, namt2));
-            // ---- filter recurrence, scalar
-            const float ya = filt_step<FILTER>(u2.x, fc, fs);
-            const float yb = filt_step<FILTER>(u2.y, fc, fs);
-            // ---- envelope segment and output gain
+            const uint32_t ha = FASTHASH ? nbc + fi * 0x9e3779b9u : (rot ^ (n + fi)) * 0x9e3779b9u;
+            const uint32_t hb = FASTHASH ? nbc + (fi + 1u) * 0x9e3779b9u : (rot ^ (n + fi + 1u)) * 0x9e3779b9u;
+            const float2 u2 = input2<FASTHASH>(F, osc2, ha, hb);
+            // ---- filter recurrence
+            const float2 y2 = filt_step2<FILTER>(u2, fc, fc, fs);
+            // ---- envelope segment (old/simdtest.rs:270-330) and output gain (process.rs:373-378)
             float2 g2;
-            if (GCONST) g2 = ey0_2;
-            else {
-                const float xb = __fadd_rn(xf, 1.0f);
+            if (GMODE == G_CONST) g2 = splat2(F.ey0);
+            else if (GMODE == G_LINE) {
+                // es * (x + nex0) + ey0, the add through an fma by one (see the hazard note)
+                g2 = s2c::vaddp(pmul2(splat2(F.es), padd2(xf2, splat2(F.nex0))), splat2(F.ey0), one);
+                xf2 = padd2(xf2, splat2(2.0f));
+            } else {
+                const uint32_t ne = n + fi;
                 if (ne + 2u <= sg.nend) {
                     // both frames inside the current segment: its line, bit-exact (see SegEnv)
-                    g2.x = seg_eval(sg, xf);
-                    g2.y = seg_eval(sg, xb);
+                    g2.x = seg_eval(sg, xf2.x);
+                    g2.y = seg_eval(sg, xf2.y);
                 } else {
                     // a stage boundary: the full stage chain for these two frames, then the next segment
-                    g2.x = env_x16(A, xf);
-                    g2.y = env_x16(A, xb);
-                    sg = seg_env(A, ne + 2u);
+                    g2.x = env_x16(*amp, xf2.x);
+                    g2.y = env_x16(*amp, xf2.y);
+                    sg = seg_env(*amp, ne + 2u);
                 }
-                ne += 2u;
-                xf = __fadd_rn(xf, 2.0f);
+                xf2 = padd2(xf2, splat2(2.0f));
             }
-            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(make_float2(ya, yb), g2);
+            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
             o4[2 * h] = out2.x;
             o4[2 * h + 1] = out2.y;
         }
@@ -659,88 +628,184 @@ __device__ __forceinline__ void chunk_fast_tp(FastV<1>& F, const EnvP* __restric
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
 }
 
-// Modulated-cutoff chunk (one voice per lane): the period is constant but the mod envelope is moving,
-// so the cutoff — and with it the filter coefficients — changes every frame (process.rs:148-152,
-// 363-371; the first 200 ms of every note of the default patch, synth.rs:141-150).  Everything else
-// keeps its fast form; envelopes are evaluated per frame with their full stage chain.
-// SHARED: every voice of the warp has the same cutoff trajectory (same cutoff, damping, modulation amount, mod
-// envelope and frame offset — a detune / pitch sweep of one patch, BASELINE config 5), so the 32 frames'
-// coefficients were computed once, one frame per lane, into `ctab` ([c0 | c1 | c2 | fl bits][32], see
-// modcut_coefficients): the same make_filt on the same inputs, hence the same bits, at 1/32 of the work.
-template <int FILTER, int KIND, int TRACE, bool SHARED, class ENV>
-__device__ __forceinline__ void chunk_modcut(FastV<1>& F, const ENV* __restrict__ amp, const ENV* __restrict__ mod,
-                                             float lpf, float amt_lpf, float damp, float sr, FiltC& fc, uint32_t kind,
-                                             uint32_t rot, uint32_t n0, float* __restrict__ row, const float* sintab,
-                                             const float* __restrict__ ctab) {
-    const ENV A = *amp;
-    ENV M;
-    if (!SHARED) M = *mod;
-    SegEnv sa = seg_env(A, n0), sm = {0.0f, 0.0f, 0.0f, 0u};
-    if (!SHARED) sm = seg_env(M, n0);
-    OscC o;
-    o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
+// Per-lane inputs of a moving-cutoff chunk (registers, valid for one chunk).
+struct MovV {
+    CutP cp;
+    float mes, mnex0, mey0;      // the mod envelope's segment line (the whole chunk lies inside it)
+    bool moving;                 // false: this lane's cutoff rests (F.c0 .. F.c2) while others of the warp move
+};
+
+// Moving-cutoff chunk, packed: the period is constant but the mod envelope is in a ramp, so the cutoff — and with
+// it the filter coefficients — changes every frame (process.rs:148-152, 363-371; the first 200 ms of every note of
+// the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every active lane): the
+// chunk starts at a multiple of 32 frames, lies inside one segment of the mod envelope, and (second-order
+// filters) its window W is valid.  Coefficients of frames (i, i + 1) in packed arithmetic (s2_cutoff.h), the amp
+// envelope per pair as in G_ANY.  MIXED: some lanes' cutoffs rest; they select their constants.
+template <int FILTER, int KIND, bool MIXED, int TRACE>
+__device__ __forceinline__ void chunk_modcut_pk(FastV& F, const EnvP* __restrict__ amp, const MovV& mv, const s2c::Window& W,
+                                                float one, uint32_t kind, uint32_t rot, uint32_t n0,
+                                                float* __restrict__ row, const float* sintab) {
+    static_assert(FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
+    const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
+    uint32_t n = n0;
+    float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
+    SegEnv sg = seg_env(*amp, n0);
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     float ph = F.ph;
-    uint32_t n = n0;
-    float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
         float o4[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float g;
-            if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(A, xf); sa = seg_env(A, n + 1u); }
-            if (SHARED) {
-                const int fi = 4 * j + i;
-                fc.c0 = ctab[fi]; fc.c1 = ctab[32 + fi]; fc.c2 = ctab[64 + fi];
+        for (int h = 0; h < 2; h++) {
+            // ---- coefficients of the two frames
+            const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
+            const float2 th2 = s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0);
+            float2 c0, c1, c2;
+            if (FILTER == FILT_ONE_POLE) {
+                c0 = s2c::exp_neg_fast<float2>(th2);
+                c1 = pfma2(c0, splat2(-one), splat2(1.0f));           // 1 - k, one rounding (exact product)
+                c2 = splat2(0.0f);
             } else {
-                float m;
-                if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
-                // branch-free on purpose: 2^(m * 0) * f == f exactly, and re-deriving unchanged coefficients
-                // gives the same bits, so voices whose cutoff does not move lose nothing and the warp does not
-                // diverge around the binary64 code
-                const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
-                make_filt<FILTER>(fc, fl, damp, sr);
+                float2 s2v, co2;
+                s2c::window_sincos<float2>(W, th2, &s2v, &co2);
+                s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2v, co2, mv.cp.hd, one, &c0, &c1, &c2);
             }
-            const float ph0 = ph;
-            const float osc = osc_step<KIND, false>(kind, o, ph, sintab);
-            const float nz = noise_fast(rot, n);
-            const float u = __fadd_rn(__fadd_rn(osc, F.gain), __fadd_rn(nz, F.namt));
-            const float y = filt_step<FILTER>(u, fc, fs);
-            o4[i] = TRACE == TRACE_PHASE ? ph0 : __fmul_rn(y, g);
-            n += 1u;
-            xf = __fadd_rn(xf, 1.0f);
+            FiltC ca, cb;
+            if (MIXED && !mv.moving) {
+                ca.c0 = cb.c0 = F.c0; ca.c1 = cb.c1 = F.c1; ca.c2 = cb.c2 = F.c2;
+            } else {
+                ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
+                cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
+            }
+            // ---- oscillator, noise, filter
+            const float pa = ph;
+            const float pb = wrap_unit(__fadd_rn(pa, F.d));
+            ph = wrap_unit(__fadd_rn(pb, F.d));
+            const float2 ph2 = make_float2(pa, pb);
+            const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
+            const uint32_t ha = (rot ^ n) * 0x9e3779b9u, hb = (rot ^ (n + 1u)) * 0x9e3779b9u;
+            const float2 u2 = input2<false>(F, osc2, ha, hb);
+            const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
+            // ---- amp envelope
+            float2 g2;
+            if (n + 2u <= sg.nend) {
+                g2 = s2c::vaddp(pmul2(splat2(sg.es), padd2(xf2, splat2(sg.nex0))), splat2(sg.ey0), one);
+            } else {
+                g2.x = env_x16(*amp, xf2.x);
+                g2.y = env_x16(*amp, xf2.y);
+                sg = seg_env(*amp, n + 2u);
+            }
+            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
+            o4[2 * h] = out2.x;
+            o4[2 * h + 1] = out2.y;
+            n += 2u;
+            xf2 = padd2(xf2, splat2(2.0f));
         }
         *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
-    if (SHARED) fc.fl_bits = __float_as_uint(ctab[96 + kChunk - 1]);      // keep the memo key of the last frame
+    F.ph = ph;
+    F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+}
+
+// Moving-cutoff chunk, one frame at a time: any alignment, any filter, windows made on demand (valid or not).
+// The chunk lies inside one segment `sm` of the mod envelope.  The same per-frame functions as the packed form,
+// hence the same bits.
+// SHARED: every voice of the warp has the same cutoff trajectory (same cutoff, damping, modulation amount, mod
+// envelope and frame offset — a detune / pitch sweep of one patch, BASELINE config 5), so the 32 frames'
+// coefficients were computed once, one frame per lane, into `ctab` ([c0 | c1 | c2][32], see modcut_coefficients).
+template <int FILTER, int KIND, int TRACE, bool SHARED>
+__device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvP* __restrict__ amp, const MovV& mv, const SegEnv& sm,
+                                                float one, uint32_t kind, uint32_t rot, uint32_t n0,
+                                                float* __restrict__ row, const float* sintab, const float* __restrict__ ctab) {
+    SegEnv sa = seg_env(*amp, n0);
+    OscC o;
+    o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
+    FiltS fs = {F.x1, F.x2, F.y1, F.y2};
+    FiltC fc;
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
+    s2c::Window W;
+    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    float ph = F.ph;
+    uint32_t n = n0;
+    float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
+#pragma unroll 1
+    for (int i = 0; i < kChunk; i++) {
+        float g;
+        if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(*amp, xf); sa = seg_env(*amp, n + 1u); }
+        if (SHARED) { fc.c0 = ctab[i]; fc.c1 = ctab[32 + i]; fc.c2 = ctab[64 + i]; }
+        else if (mv.moving) moving_coefs<FILTER>(fc, W, sm, mv.cp, one, n, seg_eval(sm, xf));
+        const float ph0 = ph;
+        const float osc = osc_step<KIND, false>(kind, o, ph, sintab);
+        const float nz = noise_fast(rot, n);
+        const float u = __fadd_rn(__fadd_rn(osc, F.gain), __fadd_rn(nz, F.namt));
+        const float y = filt_step<FILTER>(u, fc, fs);
+        row[i] = TRACE == TRACE_PHASE ? ph0 : __fmul_rn(y, g);
+        n += 1u;
+        xf = __fadd_rn(xf, 1.0f);
+    }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
 }
 
 // One frame per lane: the filter coefficients of frames n0 .. n0 + 31 of a cutoff trajectory shared by the warp.
-template <int FILTER, class ENV>
-__device__ __forceinline__ void modcut_coefficients(const ENV& M, float lpf, float amt_lpf, float damp, float sr,
-                                                    uint32_t n0, int lane, float* __restrict__ ctab) {
-    const float m = env_x16(M, __uint2float_rn(n0 + (uint32_t)lane));
-    const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
+template <int FILTER>
+__device__ __forceinline__ void modcut_coefficients(const SegEnv& sm, const CutP& cp, float one, uint32_t n0, int lane,
+                                                    float* __restrict__ ctab) {
+    const uint32_t n = n0 + (uint32_t)lane;
+    s2c::Window W;
+    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
     FiltC c;
-    make_filt<FILTER>(c, fl, damp, sr);
-    ctab[lane] = c.c0; ctab[32 + lane] = c.c1; ctab[64 + lane] = c.c2; ctab[96 + lane] = fl;
+    moving_coefs<FILTER>(c, W, sm, cp, one, n, seg_eval(sm, __uint2float_rn(n)));
+    ctab[lane] = c.c0; ctab[32 + lane] = c.c1; ctab[64 + lane] = c.c2;
+}
+
+// Moving-cutoff state of the general per-frame path (one voice, any frame order inside a chunk)
+struct MovG {
+    CutP cp;
+    SegEnv sm;           // the mod-envelope segment of the last moving frame (nbeg > nend: none yet)
+    s2c::Window W;
+};
+__device__ __forceinline__ void movg_init(MovG& g, float lpf, float amt_lpf, float damp, float sr) {
+    g.cp = make_cutp(lpf, amt_lpf, damp, sr);
+    g.sm.nbeg = 1u; g.sm.nend = 0u; g.sm.es = g.sm.nex0 = g.sm.ey0 = 0.0f; g.sm.stage = 4;
+    g.W.k = 0xffffffffu; g.W.valid = 0u; g.W.thc = 0.0f; g.W.Ah = g.W.Al = g.W.Bh = g.W.Bl = 0.0f;
+}
+
+// Filter coefficients of x16 frame n (m = its mod-envelope value): the moving evaluation while the mod envelope ramps
+// and the cutoff follows it, the resting one (memoised by the cutoff's bits) otherwise.  Below 2^24 the frame offset
+// is exact in f32 and the segment arithmetic holds; beyond, the envelope rests anyway.
+template <int FILTER>
+__device__ __forceinline__ void x16_coefs(FiltC& c, MovG& mg, const EnvP& M, float lpf, float amt_lpf, float damp,
+                                          float sr, float one, uint32_t n, float m) {
+    bool moving = false;
+    if (amt_lpf != 0.0f && n < (1u << 24)) {
+        if (n < mg.sm.nbeg || n >= mg.sm.nend) mg.sm = seg_env(M, n);
+        moving = stage_moves(mg.sm.stage);
+    }
+    if (moving) {
+        moving_coefs<FILTER>(c, mg.W, mg.sm, mg.cp, one, n, m);
+    } else {
+        const float fl = modulate_freq(lpf, m, amt_lpf);
+        if (__float_as_uint(fl) != c.fl_bits) make_filt<FILTER>(c, fl, damp, sr);
+    }
 }
 
 // General frame: the normative per-sample semantics, x16 or scalar-tail flavour.
 template <int FILTER, int TRACE>
-__device__ __forceinline__ float general_frame(const Lane& L, float sr, uint32_t n, bool scalar_sem, OscC& o, FiltC& c,
-                               float& ph, FiltS& fs, const float* sintab) {
+__device__ __forceinline__ float general_frame(const Lane& L, float sr, float one, uint32_t n, bool scalar_sem, OscC& o,
+                                               FiltC& c, MovG& mg, float& ph, FiltS& fs, const float* sintab) {
     const float x = __uint2float_rn(n);           // offset as f32
     float g, m;
     if (!scalar_sem) { g = env_x16(L.amp, x); m = env_x16(L.mod, x); }
     else { g = env_scalar(L.amp, x); m = env_scalar(L.mod, x); }
     const float fo = modulate_freq(L.pitch, m, L.amt_osc);
-    const float fl = modulate_freq(L.lpf, m, L.amt_lpf);
     if (__float_as_uint(fo) != o.fo_bits) make_osc(o, fo, sr);
-    if (__float_as_uint(fl) != c.fl_bits) make_filt<FILTER>(c, fl, L.damp, sr);
+    if (!scalar_sem) {
+        x16_coefs<FILTER>(c, mg, L.mod, L.lpf, L.amt_lpf, L.damp, sr, one, n, m);
+    } else {
+        const float fl = modulate_freq(L.lpf, m, L.amt_lpf);
+        if (__float_as_uint(fl) != c.fl_bits) make_filt<FILTER>(c, fl, L.damp, sr);
+    }
     const float ph0 = ph;
     const float osc = osc_step<-1, true>(L.kind, o, ph, sintab);
     const float nz = noise_literal(L.rot, n);
@@ -753,50 +818,27 @@ __device__ __forceinline__ float general_frame(const Lane& L, float sr, uint32_t
 
 // ------------------------------------------------------------------------------------------
 
-template <int NV, int FILTER, int KIND, int TRACE>
-__device__ __forceinline__ void chunk_fast_dispatch(bool gconst, bool namt0, bool aligned8, FastV<NV>& F, const EnvP* amp0,
-                                                    const uint32_t (&kind)[NV],
-                                                    const uint32_t (&rot)[NV], const uint32_t (&n)[NV],
-                                                    float* tile, int lane, const float* sintab) {
-    if constexpr (NV == 1) {
-        float* row = tile + lane * kTileStride;
-        // the sustain / tail steady state gets the fully specialised loop; envelope ramps, added noise
-        // amounts and odd offsets are a small share of a render and share more general variants
-        if (gconst && namt0 && aligned8) chunk_fast_tp<FILTER, KIND, true, true, true, TRACE>(F, amp0, kind[0], rot[0], n[0], row, sintab);
-        else if (gconst) chunk_fast_tp<FILTER, KIND, true, false, false, TRACE>(F, amp0, kind[0], rot[0], n[0], row, sintab);
-        else chunk_fast_tp<FILTER, KIND, false, false, false, TRACE>(F, amp0, kind[0], rot[0], n[0], row, sintab);
-    } else {
-        if (gconst) {
-            if (namt0) chunk_fast<NV, FILTER, KIND, true, true, TRACE>(F, kind, rot, n, tile, lane, sintab);
-            else chunk_fast<NV, FILTER, KIND, true, false, TRACE>(F, kind, rot, n, tile, lane, sintab);
-        } else {
-            chunk_fast<NV, FILTER, KIND, false, false, TRACE>(F, kind, rot, n, tile, lane, sintab);
-        }
-    }
-}
-
 // Per-voice state that only the classifier, the general path and the epilogue touch.  It lives in
-// shared memory ("coefficient and state tiles"), not in registers: the fast loop then owns the whole
-// 128-register budget that keeps all 13.8 warps per SM resident.  An odd word count keeps the 32
+// shared memory ("coefficient and state tiles"), not in registers: the fast loops then own the whole
+// register budget that keeps all 13.8 warps per SM resident.  An odd word count keeps the 32
 // lanes of a warp on distinct banks.
 struct Cold {
     Lane L;
     OscC oc;
     FiltC fc;
-    FastEnv fe;
-    uint32_t n_safe;       // fast constants are valid for frame offsets [.., n_safe)
-    uint32_t n_gc;         // the amp envelope is a constant (sustain / end) for offsets [.., n_gc); 0 = ramping
+    SegEnv msg;            // the mod-envelope ramp the voice's moving cutoff is in (flags bit 2)
+    float theta0;          // (2 pi cutoff) / sr
+    uint32_t n_safe;       // the resting constants (period, cutoff) are valid for frame offsets [.., n_safe)
     uint32_t vi;           // slot index (state/params column)
     uint32_t out_row;      // caller-visible voice index, 0xffffffff = no such voice
-    uint32_t flags;        // bit 0 active, bit 1 mod envelope matters
+    uint32_t flags;        // bit 0 active, bit 1 mod envelope matters, bit 2 the cutoff is moving (see msg)
 };
 constexpr int kColdWords = (sizeof(Cold) / 4) | 1;
 constexpr int kRowPtrWords = 2;    // one 64-bit output-row base per tile row (0 = the row has no output)
-constexpr int kCoefWords = 128;    // shared moving-cutoff coefficients of one chunk: [c0 | c1 | c2 | fl][32]
+constexpr int kCoefWords = 96;     // shared moving-cutoff coefficients of one chunk: [c0 | c1 | c2][32]
 
-template <int NV>
 __host__ __device__ constexpr size_t warp_smem_floats() {
-    return 32 * NV * kTileStride + 32 * NV * kColdWords + 32 * NV * kRowPtrWords + kCoefWords;
+    return 32 * kTileStride + 32 * kColdWords + 32 * kRowPtrWords + kCoefWords;
 }
 
 }  // namespace s2

@@ -47,18 +47,18 @@ struct RenderArgs {
     size_t row_stride;
     float* bus_partials;   // [n_warps][frames] or nullptr
     uint32_t has_sine;     // any voice uses the table oscillator -> stage SIN_TABLE in smem
+    float one;             // 1.0f, opaque to the compiler (s2_cutoff.h: vaddp)
+    uint32_t force_path;   // test hook (S2_FORCE_PATH): 0 = normal, 1 = moving-cutoff chunks one frame at a time,
+                           // 2 = every chunk through the general per-frame path
 };
 
 constexpr int kWarpsPerBlock = 1;
 constexpr int kChunk = 32;          // frames per warp tile
 constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, conflict-free STS.128/LDS.128
 
-// Launchers (s2_kernels.cu).  Return the cudaError_t of the launch.
-// nv = voices per lane: 1 (scalar FP32) or 2 (packed f32x2); a warp renders 32*nv consecutive slots.
-cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, int nv, cudaStream_t stream);
-uint32_t render_warps(uint32_t n_voices, int nv);
-// producer/consumer warp pair per 32 voices (s2_kernel_pc.cu); same arguments, one voice per lane
-cudaError_t launch_render_pc(const RenderArgs& a, uint32_t filter_kind, cudaStream_t stream);
+// Launchers (s2_kernels.cu).  Return the cudaError_t of the launch.  A warp renders 32 consecutive slots.
+cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream);
+uint32_t render_warps(uint32_t n_voices);
 // time-split rendering of narrow banks (s2_kernel_ts.cu): the phase pre-pass writes, for each of the block's 32
 // time segments, the phase of its first frame and of the two frames before it to seg_phase[n_voices][3][32];
 // the render consumes it.

@@ -72,13 +72,14 @@ __global__ void __launch_bounds__(32) ts_phase_kernel(const RenderArgs a, float*
 }
 
 template <int FILTER, bool GCONST>
-__device__ __forceinline__ void ts_chunk_kind(FastV<1>& F, const EnvP* amp, uint32_t kind, uint32_t rot, uint32_t n,
+__device__ __forceinline__ void ts_chunk_kind(FastV& F, const EnvP* amp, float one, uint32_t kind, uint32_t rot, uint32_t n,
                                               float* row, const float* sintab) {
+    constexpr int G = GCONST ? G_CONST : G_ANY;
     switch (kind) {                       // warp-uniform: a warp is one voice
-    case 0: chunk_fast_tp<FILTER, 0, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
-    case 1: chunk_fast_tp<FILTER, 1, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
-    case 2: chunk_fast_tp<FILTER, 2, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
-    default: chunk_fast_tp<FILTER, 3, GCONST, false, false, TRACE_NONE>(F, amp, kind, rot, n, row, sintab); break;
+    case 0: chunk_fast_tp<FILTER, 0, G, false, TRACE_NONE>(F, amp, one, kind, rot, n, row, sintab); break;
+    case 1: chunk_fast_tp<FILTER, 1, G, false, TRACE_NONE>(F, amp, one, kind, rot, n, row, sintab); break;
+    case 2: chunk_fast_tp<FILTER, 2, G, false, TRACE_NONE>(F, amp, one, kind, rot, n, row, sintab); break;
+    default: chunk_fast_tp<FILTER, 3, G, false, TRACE_NONE>(F, amp, one, kind, rot, n, row, sintab); break;
     }
 }
 
@@ -93,29 +94,32 @@ __device__ __forceinline__ M22 shfl_up(const M22& m, int off) {
 }
 
 // One sweep over a lane's segment with a MOVING cutoff (the mod envelope is in a ramp: the first 200 ms of every
-// note of the default patch).  Per frame, exactly the moving-cutoff chunk of the wide-bank kernel (chunk_modcut:
-// envelopes by stage line, 2^(m*amt), make_filt, oscillator, noise, filter step); the first sweep also
+// note of the default patch).  Per frame, exactly the per-frame functions of the wide-bank kernel (x16_coefs:
+// envelopes by stage line, the moving or resting coefficient evaluation, oscillator, noise, filter step); the first sweep also
 // accumulates the product of the per-frame state maps — k_n for the one-pole, M_n = [[2g_n, -2b_n], [1, 0]] for
 // the biquad — which is the segment's map for the scan.  WRITE: second sweep, output through the tile.
 template <int FILTER, bool WRITE>
 __device__ __forceinline__ void ts_moving_sweep(const EnvP& A, const EnvP& M, float lpf, float amt_lpf, float damp,
-                                                float sr, const OscC& oc, uint32_t kind, uint32_t rot, float gain,
+                                                float sr, float one, const OscC& oc, uint32_t kind, uint32_t rot, float gain,
                                                 float namt, uint32_t nl, uint32_t L, float& ph, FiltS& fs, float& kprod,
                                                 M22& mprod, float* tile, int lane, float* __restrict__ gout,
                                                 const float* sintab) {
     const int q = lane >> 3, c4 = (lane & 7) * 4;
     float* row = tile + lane * kTileStride;
-    SegEnv sa = seg_env(A, nl), sm = seg_env(M, nl);
+    SegEnv sa = seg_env(A, nl);
     uint32_t n = nl;
     float xf = __uint2float_rn(nl);
     FiltC fc;
+    fc.c0 = fc.c1 = fc.c2 = 0.0f; fc.fl_bits = kNoKey;
+    MovG mg;
+    movg_init(mg, lpf, amt_lpf, damp, sr);
+    mg.sm = seg_env(M, nl);
     for (uint32_t c = 0; c < L; c += kChunk) {
-#pragma unroll 2
+#pragma unroll 1
         for (int i = 0; i < kChunk; i++) {
-            float m;
-            if (n < sm.nend) m = seg_eval(sm, xf); else { m = env_x16(M, xf); sm = seg_env(M, n + 1u); }
-            const float fl = __fmul_rn(pow2_ref(__fmul_rn(m, amt_lpf)), lpf);
-            make_filt<FILTER>(fc, fl, damp, sr);
+            if (n >= mg.sm.nend) mg.sm = seg_env(M, n);
+            const float m = seg_eval(mg.sm, xf);
+            x16_coefs<FILTER>(fc, mg, M, lpf, amt_lpf, damp, sr, one, n, m);
             const float osc = osc_step<-1, false>(kind, oc, ph, sintab);
             const float u = __fadd_rn(__fadd_rn(osc, gain), __fadd_rn(noise_fast(rot, n), namt));
             const float y = filt_step<FILTER>(u, fc, fs);
@@ -192,11 +196,11 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     make_osc(oc, P[P_PITCH * vp], sr);
     make_filt<FILTER>(fc, fl, P[P_DAMP * vp], sr);
 
-    FastV<1> F;
+    FastV F;
     F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
     F.gain = P[P_GAIN * vp]; F.namt = P[P_NOISE * vp];
-    F.c0 = fc.c0; F.c1 = FILTER == 0 ? fc.c1 : -fc.c1; F.c2 = fc.c2;       // biquad: the loop adds -2*beta*y2
-    F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f;
+    F.c0 = fc.c0; F.c1 = fc.c1; F.c2 = fc.c2;
+    F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f; F.seg_end = 0u;
     const float* __restrict__ sp = seg_phase + (size_t)slot * (3 * kSegs);
     const float ph0 = sp[lane];
     const uint32_t nl = n0 + (uint32_t)lane * L;             // this lane's first frame offset
@@ -223,13 +227,13 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     if (MOVING) {
         float ph = ph0;
         FiltS fs = {x1_in, x2_in, 0.0f, 0.0f};
-        ts_moving_sweep<FILTER, false>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, oc, kind, rot, F.gain, F.namt,
+        ts_moving_sweep<FILTER, false>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, a.one, oc, kind, rot, F.gain, F.namt,
                                        nl, L, ph, fs, kprod, mprod, tile, lane, gout, sintab);
         F.y1 = fs.y1; F.y2 = fs.y2;
     } else {
         F.ph = ph0;
         F.x1 = x1_in; F.x2 = x2_in; F.y1 = 0.0f; F.y2 = 0.0f;
-        for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, kind, rot, nl + c, row, sintab);
+        for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, a.one, kind, rot, nl + c, row, sintab);
     }
 
     // ---- the segment maps compose left to right: inclusive Hillis-Steele scan over the lanes
@@ -284,14 +288,14 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     if (MOVING) {
         float ph = ph0;
         FiltS fs = {x1_in, x2_in, y1_in, y2_in};
-        ts_moving_sweep<FILTER, true>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, oc, kind, rot, F.gain, F.namt,
+        ts_moving_sweep<FILTER, true>(A, M, P[P_LPF * vp], amt_lpf, P[P_DAMP * vp], sr, a.one, oc, kind, rot, F.gain, F.namt,
                                       nl, L, ph, fs, kprod, mprod, tile, lane, gout, sintab);
         F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
     } else {
         F.ph = ph0;
         F.x1 = x1_in; F.x2 = x2_in; F.y1 = y1_in; F.y2 = y2_in;
         for (uint32_t c = 0; c < L; c += kChunk) {
-            ts_chunk_kind<FILTER, false>(F, &A, kind, rot, nl + c, row, sintab);
+            ts_chunk_kind<FILTER, false>(F, &A, a.one, kind, rot, nl + c, row, sintab);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; i++) {
