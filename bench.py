@@ -7,15 +7,24 @@
 Workload (BASELINE config 3, per GPU): 65,536 voices, oscillator + resonant biquad (2nd-order
 low-pass) + ADSR, 48 kHz, 60 s = 2,880,000 frames per voice, streamed as 4,096-frame blocks through
 a ring of two 1 GiB voice-major output buffers with the DSP state carried on the device.
-One "step" = one block of every voice (the last of the default 704 steps is the 512-frame
-remainder).  N GPUs = N x 65,536 voices, each rank owning a contiguous voice range ("weak").
+One "step" = one block of every voice, FROM NOTE-ON: --steps K renders the first K * 4,096 frames of the
+60 s render (the default 704 steps are the whole render; the last step is the 512-frame remainder).  The first
+200 ms after note-on (2.3 steps) hold the mod-envelope sweep of the cutoff, the next ~1 s the attack / decay
+ramps; `step_ms` in the result shows them.  N GPUs = N x 65,536 voices, each rank owning a contiguous voice
+range ("weak").
 
   value      device-resident throughput: inputs (voice table, state) already in HBM, CUDA events
              around the K steps on the launching stream, max over ranks.
+  step_ms    per-step completion intervals (CUDA events after every step, rank 0).
+  parity     after the timed region: the CPU oracle renders a sample of the timed voices over the same frames;
+             final oscillator phase bit-for-bit, max |err| and SNR of the last block.
   e2e        the same render driven through the host-buffer C-ABI calls a streaming caller uses:
              every step uploads the note-off table (pinned host -> device), renders the block
              (per-voice output stays in the device ring) with the mono mix, and copies the mix
              (the `Synth::sample` result) back to pinned host memory.
+  extra      the other BASELINE configs on the same GPU(s): config 2 (1,024 voices, time-split), config 5
+             (32,768 patch variants) at N = 1; config 4 (262,144 voices over N GPUs, master bus, one NCCL
+             reduce) at N > 1.
   roofline   HBM: 4 algorithmic bytes per voice-sample (one f32 store, touched once)
   cpu_baseline / --impl reference
              the CPU port of the reference path (oracle/, "port": the Rust reference cannot be
@@ -55,6 +64,8 @@ def parse():
     ap.add_argument("--pipeline", type=int, default=4,
                     help="render each GPU's bank as this many voice ranges on internal streams (1 = single stream)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / 4 / 5 measurements")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
@@ -109,7 +120,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.001)
 
     def __enter__(self):
         if self._nv:
@@ -203,11 +214,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from synth2_b200 import bankgen
+    from synth2_b200 import bankgen     # numpy only: the product library (libs2cuda.so) is never loaded by this arm
     cores = os.cpu_count() or 1
     nv = max(cores * 64, 1024)          # enough voices per thread that thread start-up does not show (same as cpu_baseline)
-    voices = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
     oracle = cpu_oracle()
+    voices = bankgen.make_bank(nv, RENDER_FRAMES, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD,
+                               pitches=oracle.pitch_table())
     st = oracle.bank_init_states(voices)
     frames = step_frames(args.steps, args.block)
     for _ in range(args.warmup):
@@ -225,8 +237,9 @@ def run_reference(args):
         "unit": "voice-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config 3: osc + resonant biquad + ADSR, 48 kHz, 4096-frame blocks (CPU sample of the 65,536-voice bank)",
-                   "voices": nv, "block_frames": args.block},
+        "config": {"workload": f"config 3: osc + resonant biquad + ADSR, 48 kHz, 4096-frame blocks; CPU sample: {nv} voices of the "
+                               f"65,536-voice bank over the same first {sum(frames)} frames from note-on",
+                   "voices": nv, "block_frames": args.block, "render_frames": sum(frames)},
         "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -234,6 +247,179 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# parity of the timed render, and the other BASELINE configs
+
+PARITY_VOICES = 64
+
+
+def parity_of_timed_render(voices, final_state, last_block, frames, np):
+    """The oracle (allowed here: the checker, after the timed region) renders PARITY_VOICES voices of the timed bank
+    over the same frames from note-on; compared with the GPU: final oscillator phase and frame offset bit-for-bit,
+    the last block's rows by max |err| (unscaled, and over the reference peak) and SNR."""
+    oracle = cpu_oracle()
+    V = voices.shape[0]
+    total = sum(frames)
+    # half spread evenly over the bank, half from the corner where the second-order low-pass is least
+    # forgiving in binary32: the lowest cutoff x damping products among the voices whose cutoff follows the mod envelope
+    even = np.linspace(0, V - 1, PARITY_VOICES // 2).astype(np.int64)
+    corner_score = voices["lpf_freq_hz"].astype(np.float64) * voices["damping"] + np.where(voices["mod_env_to_lpf_freq"] != 0, 0.0, 1e9)
+    corner = np.argsort(corner_score, kind="stable")[:PARITY_VOICES // 2]
+    idx = np.unique(np.concatenate([even, corner]))
+    sub = np.ascontiguousarray(voices[idx])
+    st = oracle.bank_init_states(sub)
+    t0 = time.perf_counter()
+    if total > frames[-1]:
+        oracle.bank_render(sub, st, SR, FILTER_BIQUAD, total - frames[-1], want_voices=False, want_bus=False,
+                           nthreads=os.cpu_count() or 1)
+    ref, _ = oracle.bank_render(sub, st, SR, FILTER_BIQUAD, frames[-1], want_bus=False, nthreads=os.cpu_count() or 1)
+    dt = time.perf_counter() - t0
+    got = last_block[idx.tolist(), :frames[-1]].cpu().numpy()
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    per_voice = err.max(axis=1)
+    peak = float(np.max(np.abs(ref)))
+    p_err, p_ref = float(np.sum(err * err)), float(np.sum(ref.astype(np.float64) ** 2))
+    snr = float("inf") if p_err == 0.0 else 10.0 * float(np.log10(max(p_ref, 1e-300) / p_err))
+    gs = final_state[idx]
+    over = [{"voice": int(idx[i]), "cutoff_hz": float(sub["lpf_freq_hz"][i]), "damping": float(sub["damping"][i]),
+             "max_abs_err": float(per_voice[i])} for i in np.argsort(-per_voice)[:8] if per_voice[i] > 1e-4]
+    return {"voices_checked": int(idx.size), "frames": int(total), "compared": f"last block ({frames[-1]} frames) and final state",
+            "phase_bit_exact": bool(np.array_equal(gs["phase"].view(np.uint32), st["phase"].view(np.uint32))),
+            "frame_offset_equal": bool(np.array_equal(gs["frame_offset"], st["frame_offset"])),
+            "max_abs_err": float(per_voice.max()), "ref_peak": peak,
+            "max_abs_err_over_ref_peak": float(per_voice.max()) / max(peak, 1e-30), "snr_db": snr,
+            "voices_over_1e-4_unscaled": over, "oracle_seconds": dt}
+
+
+def _timed(torch, stream, bank, body):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    body()
+    bank.join(stream)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) * 1e-3
+
+
+def _peak_gbs():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def _rate(voices, frames, seconds, **kw):
+    vs = voices * frames / seconds
+    return {"voices": voices, "frames_per_voice": frames, "seconds": seconds, "value": vs, "unit": "voice-samples/s",
+            "roofline_frac": vs * BYTES_PER_VOICE_SAMPLE / 1e9 / _peak_gbs(), **kw}
+
+
+def extra_config2(s2, bankgen, torch, stream, dev_index):
+    """BASELINE config 2: 1,024 saw/square voices + one-pole low-pass, 4,096-frame buffers, time-split kernels.
+    64 blocks from note-on (cutoff sweep + ramps), then 64 more (sustain); 16 rotating output buffers so a
+    16 MiB block does not simply sit in the 126 MB L2."""
+    V, T, blocks = 1024, 4096, 64
+    voices = bankgen.make_bank(V, 4 * 2 * blocks * T)
+    bank = s2.VoiceBank(voices, SR, s2.FILTER_ONE_POLE, device=dev_index, stream=stream)
+    bank.set_time_split(True)
+    ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(16)]
+    st = bank.get_state()
+    for i in range(4):
+        bank.render(T, ring[i & 15], T, None)
+    bank.set_state(st)
+    n0 = bank.time_split_blocks
+    sec_a = _timed(torch, stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
+    sec_b = _timed(torch, stream, bank, lambda: [bank.render(T, ring[i & 15], T, None) for i in range(blocks)])
+    ts_blocks = bank.time_split_blocks - n0
+    bank.close()
+    return {"workload": "1,024 saw/square voices + one-pole low-pass, 48 kHz, 4,096-frame buffers, time-split kernels",
+            "from_note_on": _rate(V, blocks * T, sec_a, blocks=blocks, us_per_block=sec_a / blocks * 1e6),
+            "sustain": _rate(V, blocks * T, sec_b, blocks=blocks, us_per_block=sec_b / blocks * 1e6),
+            "time_split_blocks": int(ts_blocks)}
+
+
+def extra_config5(s2, bankgen, torch, stream, dev_index, seconds=2):
+    """BASELINE config 5, one GPU's share: 32,768 patch variants (32 cutoffs x 32 dampings x 32 detunes of the default
+    patch, second-order low-pass), every variant's render kept on the device; the first `seconds` s from note-on."""
+    V, total, T = bankgen.SWEEP_VARIANTS, seconds * SR, BLOCK
+    voices = bankgen.make_sweep_bank(0, 10 * SR)
+    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=dev_index, stream=stream)
+    bank.set_pipeline(4)
+    out = torch.empty((V, total), device="cuda", dtype=torch.float32)
+    st = bank.get_state()
+    for i in range(3):
+        bank.render(T, out[:, i * T:], total, None)
+    bank.set_state(st)
+
+    def body():
+        pos = 0
+        while pos < total:
+            fr = min(T, total - pos)
+            bank.render(fr, out[:, pos:], total, None)
+            pos += fr
+    sec = _timed(torch, stream, bank, body)
+    finite = bool(torch.isfinite(out[:, -T:]).all())
+    bank.close()
+    del out
+    torch.cuda.empty_cache()
+    return {"workload": f"32,768 patch variants (cutoff x resonance x detune grid of the default patch), biquad, first {seconds} s "
+                        f"from note-on, renders kept on the device ({V * total * 4 / 1e9:.1f} GB)",
+            **_rate(V, total, sec, all_finite=finite)}
+
+
+def extra_config4(s2, bankgen, torch, dist, stream, rank, world, dev_index, rank_max, barrier, seconds=2):
+    """BASELINE config 4: a 262,144-voice bank sharded over the N GPUs as contiguous voice ranges; every rank renders
+    its rows and its share of the master bus (in-kernel mix), then ONE NCCL reduce (s2_bank_reduce_bus) sums the
+    whole-render buses into rank 0's master buffer.  Three timed passes give the breakdown: rows only, rows + mix,
+    rows + mix + reduce (all inside the timed region of the third)."""
+    from synth2_b200.shard import MasterBus, voice_range
+    lo, hi = voice_range(rank, world, 262144)
+    V, T = hi - lo, BLOCK
+    blocks = (seconds * SR + T - 1) // T
+    total = blocks * T
+    voices = bankgen.make_bank(V, 10 * SR, first_voice=lo, mod_to_lpf_choices=bankgen.MOD_TO_LPF_BIQUAD)
+    bank = s2.VoiceBank(voices, SR, s2.FILTER_BIQUAD_LP, device=dev_index, stream=stream)
+    bank.set_pipeline(4)
+    ring = [torch.empty((V, T), device="cuda", dtype=torch.float32) for _ in range(2)]
+    bus = torch.zeros(total, device="cuda", dtype=torch.float32)
+    master = torch.zeros(total, device="cuda", dtype=torch.float32)
+    comm = MasterBus(rank, world, dev_index)
+    st = bank.get_state()
+    for i in range(3):
+        bank.render(T, ring[i & 1], T, bus[:T])
+    comm.reduce(bank, bus, master, root=0, stream=stream)       # warm the communicator up
+
+    def run(mix, reduce):
+        bank.set_state(st)
+        barrier()
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ev0.record(stream)
+        for i in range(blocks):
+            bank.render(T, ring[i & 1], T, bus[i * T:(i + 1) * T] if mix else None)
+        bank.join(stream)
+        ev1.record(stream)
+        if reduce:
+            comm.reduce(bank, bus, master, root=0, stream=stream)
+        ev2.record(stream)
+        barrier()
+        return rank_max(ev0.elapsed_time(ev2)) * 1e-3, rank_max(ev1.elapsed_time(ev2)) * 1e-3
+
+    t_rows, _ = run(False, False)
+    t_mix, _ = run(True, False)
+    t_all, t_reduce = run(True, True)
+    finite = bool(torch.isfinite(master).all()) if rank == 0 else True
+    comm.close()
+    bank.close()
+    vs = 262144 * total / t_all
+    return {"workload": f"262,144 voices over {world} GPUs ({V} per GPU, contiguous ranges), osc + biquad + ADSR, first {seconds} s "
+                        "from note-on; per-voice rows + in-kernel mono mix per block, then one NCCL reduce of the whole-render bus "
+                        "(s2_bank_reduce_bus) inside the timed region",
+            "value": vs, "unit": "voice-samples/s", "roofline_frac_per_gpu": vs / world * BYTES_PER_VOICE_SAMPLE / 1e9 / _peak_gbs(),
+            "blocks": blocks, "us_per_block": {"render_rows_only": t_rows / blocks * 1e6, "mix_added": (t_mix - t_rows) / blocks * 1e6,
+                                               "total": t_all / blocks * 1e6},
+            "reduce_us_total": t_reduce * 1e6, "reduce_bytes": total * 4, "master_bus": "mono (the reference mixes to one "
+            "channel and its player copies it to both, audio_player.rs:136-199)", "all_finite": finite}
+
 
 def main():
     args = parse()
@@ -291,6 +477,7 @@ def main():
     bank.set_state(state0)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in frames]
     launches0 = s2.lib().s2_launch_count()
     with ClockSampler(local) as clocks:
         ev0.record(stream)
@@ -298,7 +485,8 @@ def main():
         for i, fr in enumerate(frames):
             bank.render(fr, ring[i & 1], T, master[pos:pos + fr] if want_master else None)
             pos += fr
-        bank.join(stream)            # pipelined banks: the timing stream waits for every voice range
+            bank.join(stream)        # pipelined banks: the timing stream waits for every voice range of this step
+            step_ev[i].record(stream)
         if want_master:
             dist.reduce(master, dst=0, op=dist.ReduceOp.SUM)
         ev1.record(stream)
@@ -306,9 +494,15 @@ def main():
     launches = s2.lib().s2_launch_count() - launches0
     ms = rank_max(ev0.elapsed_time(ev1))
     value = world * V * total_frames / (ms * 1e-3)
+    step_ms = [(ev0 if i == 0 else step_ev[i - 1]).elapsed_time(step_ev[i]) for i in range(len(frames))]
     final_state = bank.get_state()
     assert np.all(final_state["frame_offset"] == total_frames)
     assert bool(torch.isfinite(ring[(len(frames) - 1) & 1][:, :frames[-1]]).all())
+
+    # ---- parity of the timed render against the CPU oracle (after the timed region) -------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_of_timed_render(voices, final_state, ring[(len(frames) - 1) & 1], frames, np)
 
     # ---- e2e: host-buffer calls, H2D + D2H inside the timed region ----------------------------
     e2e = None
@@ -351,6 +545,19 @@ def main():
                "what": "per step: note-off table H2D (pinned), render into the device ring + mono mix, mix D2H to "
                        "pinned host (the Synth::sample result), host waits for and reads the previous step's mix "
                        "(two buffers in flight, as the reference's audio_player does); wall clock"}
+    bank.close()
+    del ring, bank
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs --------------------------------------------------------------
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        if world == 1:
+            extra["config2"] = extra_config2(s2, bankgen, torch, stream, local)
+            extra["config5"] = extra_config5(s2, bankgen, torch, stream, local)
+        else:
+            extra["config4"] = extra_config4(s2, bankgen, torch, dist, stream, rank, world, local, rank_max, barrier)
 
     peaks = {}
     try:
@@ -359,12 +566,19 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    per_launch_bytes = V * T * BYTES_PER_VOICE_SAMPLE
-    kernel_ms = ms / len(frames)            # one render kernel per step is the whole timed region
+    n_ranges = max(int(args.pipeline), 1)
+    per_launch_bytes = V * T * BYTES_PER_VOICE_SAMPLE // n_ranges
     achieved = V * total_frames * BYTES_PER_VOICE_SAMPLE / (ms * 1e-3) / 1e9
+    # a step is `n_ranges` launches of the render kernel (one per voice range, on internal streams: they overlap
+    # with each other and with the neighbouring steps), so the per-launch duration that matters is the step's
+    # share: step time / launches per step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "s2::render_kernel<1,1,0> (NV=1 voice/lane, FILTER=biquad)", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": kernel_ms}
+                "traffic": None, "kernel": "s2::render_kernel<FILTER=biquad low-pass, TRACE=0>: one voice per lane, one warp per block",
+                "peak_source": peak_src, "launches_per_step": n_ranges, "algorithmic_bytes_per_launch": per_launch_bytes,
+                "algorithmic_bytes_per_step": V * T * BYTES_PER_VOICE_SAMPLE,
+                "avg_step_ms": ms / len(frames), "avg_launch_ms": ms / len(frames) / n_ranges,
+                "avg_launch_ms_note": "launches of one step overlap (4 streams): step time / launches per step, not the "
+                                      "serialised duration ncu reports for a launch running alone"}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
@@ -381,15 +595,18 @@ def main():
             "metric": "voice-samples/sec (osc+biquad, 48 kHz)", "value": value, "unit": "voice-samples/s",
             "n_gpus": world, "steps": len(frames), "warmup": max(args.warmup, 3), "ms_per_step": ms / len(frames),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 3: 65,536 voices/GPU, osc (saw/square) + resonant biquad + ADSR, 48 kHz, "
-                                   "60 s render in 4,096-frame blocks, state carried on device",
+            "config": {"workload": f"config 3: 65,536 voices/GPU, osc (saw/square) + resonant biquad + ADSR, 48 kHz, 4,096-frame "
+                                   f"blocks, state carried on device; this run renders frames [0, {total_frames}) of the 60 s render "
+                                   f"= the first {total_frames / SR:.2f} s after note-on"
+                                   + (" (the whole render)" if total_frames == RENDER_FRAMES else
+                                      " (cutoff sweep for 0.2 s, then attack / decay ramps for up to 1 s, then sustain)"),
                        "voices_per_gpu": V, "block_frames": T, "render_frames": total_frames,
                        "l2_hygiene": "each step writes a fresh 1 GiB block (ring of 2) >> 126 MB L2; no input is re-read",
                        "master_bus": bool(want_master), "pipeline_voice_ranges": int(args.pipeline)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "launches_per_step": launches / len(frames),
+            "clocks": clocks.summary(), "step_ms": [round(x, 4) for x in step_ms], "parity": parity, "extra": extra,
         })
-    bank.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -174,6 +174,30 @@ int s2_bank_join(s2_bank* bank, void* stream);
 int s2_bank_set_time_split(s2_bank* bank, int enable);
 int s2_bank_time_split_blocks(s2_bank* bank, uint64_t* blocks);
 
+/*
+ * Master bus across GPUs (BASELINE config 4; SURVEY.md 8b "s2_bank_reduce_bus(comm, ...)", 8e).  Voices are
+ * independent (synth.rs:177-199), so a bank shards as contiguous voice ranges, one bank per GPU, and the only
+ * exchange is this: ONE reduce (sum) of the per-GPU buses into the root's master buffer over NCCL / NVLink, once per
+ * render (or per >= 1 s chunk), never per block.  The reference has no collective; its mix loop is
+ * synth.rs:171-203 and the sum order across GPUs is the collective's (tolerance, not bit-for-bit).
+ *   s2_comm_unique_id   ncclGetUniqueId: 128 bytes made on one rank and shipped to the others by the host's own means
+ *   s2_comm_create      ncclCommInitRank on `device` (collective: every rank calls it)
+ *   s2_comm_adopt       wraps an ncclComm_t the host already owns (not destroyed by s2_comm_destroy)
+ *   s2_bank_reduce_bus  joins the bank's internal streams into `stream` (a cudaStream_t, NULL = default), then
+ *                       ncclReduce(d_bus_in -> d_bus_out on `root`, f32 sum) on it.  d_bus_out may be NULL off-root
+ *                       and may equal d_bus_in.  Asynchronous.
+ * NCCL is loaded at run time (dlopen libnccl.so.2); without it these return S2_ERR_NO_DEVICE.
+ */
+#define S2_COMM_UNIQUE_ID_BYTES 128
+typedef struct s2_comm s2_comm;
+int s2_comm_version(int* version);
+int s2_comm_unique_id(uint8_t* id /* [S2_COMM_UNIQUE_ID_BYTES] */);
+int s2_comm_create(const uint8_t* id, int n_ranks, int rank, int device, s2_comm** out);
+int s2_comm_adopt(void* nccl_comm, int n_ranks, int rank, int device, s2_comm** out);
+void s2_comm_destroy(s2_comm* comm);
+int s2_bank_reduce_bus(s2_bank* bank, s2_comm* comm, int root, const float* d_bus_in, float* d_bus_out, size_t frames,
+                       void* stream);
+
 /* Checkpoint / restore / test hook.  Host arrays of n_voices entries; synchronises. */
 int s2_bank_get_state(s2_bank* bank, s2_voice_state* out);
 int s2_bank_set_state(s2_bank* bank, const s2_voice_state* in);

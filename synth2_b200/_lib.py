@@ -67,6 +67,12 @@ SYMBOLS = {
     "s2_bank_set_time_split": (_i, [_vp, _i]),
     "s2_bank_time_split_blocks": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "s2_bank_trace_phase": (_i, [_vp, _sz, _vp, _sz]),
+    "s2_comm_version": (_i, [C.POINTER(_i)]),
+    "s2_comm_unique_id": (_i, [_vp]),
+    "s2_comm_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "s2_comm_adopt": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "s2_comm_destroy": (None, [_vp]),
+    "s2_bank_reduce_bus": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2_launch_count": (C.c_uint64, []),
     "s2_synth_new": (_i, [_i, C.POINTER(_vp)]),
     "s2_synth_free": (None, [_vp]),

@@ -13,7 +13,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libs2cuda.so"
 SOURCES = [CSRC / "s2_kernels.cu", CSRC / "s2_kernel_ts.cu", CSRC / "s2_capi.cu",
-           CSRC / "s2_patch.cpp", CSRC / "s2_player.cpp"]
+           CSRC / "s2_patch.cpp", CSRC / "s2_player.cpp", CSRC / "s2_nccl.cpp"]
 DEPS = SOURCES + [CSRC / "s2_internal.h", CSRC / "s2_device.cuh", CSRC / "s2_math.h", CSRC / "s2_cutoff.h",
                   CSRC / "sin_table_bits.inc",
                   PKG.parent / "include" / "s2_cuda.h"]
@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

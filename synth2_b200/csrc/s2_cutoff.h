@@ -128,8 +128,15 @@ constexpr float kThetaMax = 3.125f;                    // a valid window's centr
 // theta = 2^(m * amount) * theta0, theta0 = (2 pi cutoff) / sr (dsp_filters.rs:107 / filters.rs:21 with the sign
 // dropped; process.rs:231-250), 2^x by the hardware
 template <class T>
-S2C_FN T theta_at(T m, float amount, float theta0) {
-    return vmul(vex2(vmul(m, splat<T>(amount))), splat<T>(theta0));
+S2C_FN T sweep_at(T m, float amount) { return vex2(vmul(m, splat<T>(amount))); }
+template <class T>
+S2C_FN T theta_at(T m, float amount, float theta0) { return vmul(sweep_at<T>(m, amount), splat<T>(theta0)); }
+// theta - thc for a frame inside the window centred on thc: ONE fma of the sweep factor (exact product, one
+// rounding).  Written as an fma on purpose: ptxas contracts a packed multiply feeding a packed add anyway, and the
+// scalar and packed forms must be the same operations.
+template <class T>
+S2C_FN T delta_at(T m, float amount, float theta0, float thc) {
+    return vfma(sweep_at<T>(m, amount), splat<T>(theta0), splat<T>(-thc));
 }
 
 // num / den for den in [1, 9], |num| <= 8: reciprocal estimate, quotient, one residual correction.  nden = -den.
@@ -167,10 +174,9 @@ S2C_FN void split_hi_lo(double v, float* hi, float* lo) {
     *lo = (float)(v - (double)*hi);
 }
 
-// sin(th), cos(th) from the window (|th - thc| <= 2^-7)
+// sin(thc + d), cos(thc + d) from the window (|d| <= 2^-7)
 template <class T>
-S2C_FN void window_sincos(const Window& W, T th, T* s, T* c) {
-    const T d = vadd(th, splat<T>(-W.thc));                               // exact (Sterbenz)
+S2C_FN void window_sincos(const Window& W, T d, T* s, T* c) {
     const T z = vmul(d, d);
     const T sd = vfma(vmul(d, z), splat<T>(-0x1.555556p-3f), d);          // sin d = d - d^3 / 6
     const T w = vmul(z, splat<T>(0.5f));                                  // 1 - cos d = d^2 / 2

@@ -301,20 +301,19 @@ __device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const
 template <int FILTER>
 __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const SegEnv& sm, const CutP& cp, float one,
                                              uint32_t n, float m) {
-    const float th = s2c::theta_at<float>(m, cp.amt, cp.theta0);
     c.fl_bits = kNoKey;                                   // not a memo of any resting cutoff
     if (FILTER == FILT_ONE_POLE) {
-        const float k = s2c::exp_neg_fast<float>(th);
+        const float k = s2c::exp_neg_fast<float>(s2c::theta_at<float>(m, cp.amt, cp.theta0));
         c.c0 = k;
         c.c1 = __fsub_rn(1.0f, k);
         c.c2 = 0.0f;
         return;
     }
-    if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, th, cp.damp); return; }
+    if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp); return; }
     if ((n >> s2c::kWinShift) != W.k) make_window<FILTER>(W, sm, cp, n);
     if (W.valid) {
         float s, co;
-        s2c::window_sincos<float>(W, th, &s, &co);
+        s2c::window_sincos<float>(W, s2c::delta_at<float>(m, cp.amt, cp.theta0, W.thc), &s, &co);
         if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
             s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
         } else {
@@ -325,10 +324,10 @@ __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const Seg
         }
     } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
         float s, co;
-        s2_sincosf(th, &s, &co);
+        s2_sincosf(s2c::theta_at<float>(m, cp.amt, cp.theta0), &s, &co);
         s2c::biquad_lp_hp_any<FILTER == FILT_BIQUAD_HP>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
     } else {
-        make_filt_theta<FILTER>(c, th, cp.damp);
+        make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp);
     }
 }
 
@@ -659,15 +658,14 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const EnvP* __restrict
         for (int h = 0; h < 2; h++) {
             // ---- coefficients of the two frames
             const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
-            const float2 th2 = s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0);
             float2 c0, c1, c2;
             if (FILTER == FILT_ONE_POLE) {
-                c0 = s2c::exp_neg_fast<float2>(th2);
+                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
                 c1 = pfma2(c0, splat2(-one), splat2(1.0f));           // 1 - k, one rounding (exact product)
                 c2 = splat2(0.0f);
             } else {
                 float2 s2v, co2;
-                s2c::window_sincos<float2>(W, th2, &s2v, &co2);
+                s2c::window_sincos<float2>(W, s2c::delta_at<float2>(m2, mv.cp.amt, mv.cp.theta0, W.thc), &s2v, &co2);
                 s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2v, co2, mv.cp.hd, one, &c0, &c1, &c2);
             }
             FiltC ca, cb;

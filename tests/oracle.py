@@ -103,6 +103,11 @@ def sin_table():
     return np.ctypeslib.as_array((C.c_float * 1024).from_address(addr)).copy()
 
 
+def pitch_table():
+    """128-entry f32 table of the oracle's `note_to_pitch` (synth.rs:208-212)."""
+    return np.array([lib().s2o_note_to_pitch(n) for n in range(128)], dtype=np.float32)
+
+
 def default_config():
     cfg = np.zeros(1, dtype=LAYER_CONFIG)
     lib().s2o_default_config(_p(cfg))

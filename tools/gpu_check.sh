@@ -4,7 +4,7 @@
 tag=${1:-x}; shift
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -q -x "$@" > gpurun_out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_tests.log
+timeout 1200 python -m pytest tests -m gpu -q "$@" > gpurun_out/${tag}_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_tests.log
 tail -5 gpurun_out/${tag}_tests.log
 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${tag}_bench20.json 2> gpurun_out/${tag}_bench20.err; echo "bench20 rc=$?"
 cat gpurun_out/${tag}_bench20.json
