@@ -9,7 +9,9 @@ import pathlib
 import numpy as np
 
 PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = PKG / "libs2cuda.so"
+import os
+
+LIB_PATH = pathlib.Path(os.environ["S2_LIB"]) if os.environ.get("S2_LIB") else PKG / "libs2cuda.so"   # S2_LIB: experiments only
 
 S2_OK = 0
 S2_ERR_INVALID = -1

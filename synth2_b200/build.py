@@ -46,7 +46,8 @@ def build_lib(force=False, verbose=False):
     if not force and not stale():
         return LIB
     extra = os.environ.get("S2_NVCC_EXTRA", "").split()          # experiments, e.g. -DS2_TRIP=16
-    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
+    out = os.environ.get("S2_LIB_OUT", str(LIB))                 # experiments: a variant next to the shipped library
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", out, *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

@@ -149,8 +149,8 @@ struct s2_bank {
     size_t bus_cap = 0;          // floats
     std::vector<VoiceBook> book;  // indexed by voice
     // "Slots": device arrays are indexed by slot, not by the caller's voice index.  Banks wider than
-    // one warp are sorted by (active, oscillator kind, what follows the mod envelope, when the envelopes
-    // rest) at creation so that the 32 lanes of a warp run the same code for as long as possible; output
+    // one warp are sorted by (active, oscillator kind, when the amp envelope rests) at creation so that the
+    // 32 lanes of a warp run the same code for as long as possible, then dealt over the voice ranges; output
     // rows, state get/set and per-voice calls keep the caller's indices.  Banks of <= 32 voices keep
     // the identity order, which also keeps the bus sum in the reference's voice order.
     std::vector<uint32_t> slot_of_voice, voice_of_slot;
@@ -523,29 +523,39 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->slot_of_voice.resize(n_voices);
     for (size_t i = 0; i < n_voices; i++) b->voice_of_slot[i] = (uint32_t)i;
     if (n_voices > 32) {
-        // (inactive last) x oscillator kind x (does the cutoff / the pitch follow the mod envelope) x when the mod
-        // and the amp envelope come to rest: the 32 voices of a warp then leave the moving-cutoff chunks and the
-        // envelope ramps together instead of waiting for the slowest of a random draw.  Stable: a patch sweep keeps
-        // the variants of one cutoff trajectory next to each other.
-        struct Key { uint32_t kind, follows; float mod_rest, amp_rest; };
+        // (inactive last) x oscillator kind x when the amp envelope comes to rest: the 32 voices of a warp then leave
+        // the envelope ramps together instead of waiting for the slowest of a random draw.  Stable: a patch sweep
+        // keeps the variants of one cutoff trajectory next to each other.
+        // NOT a key: whether the cutoff follows the mod envelope.  Grouping the followers halves the warps that run
+        // moving-cutoff chunks, but a step is one launch per voice range and a range's launches run in order: the
+        // ranges of followers (1.9x the work per frame for 200 ms) fall behind the others and finish alone on a
+        // part-filled machine.  Measured on the bench bank, first 20 blocks: 6.2 ms grouped and contiguous, 7.1 ms
+        // grouped and dealt over the ranges, against mixed warps (every warp pays, all ranges in step).
+        struct Key { uint32_t kind; float amp_rest; };
         std::vector<Key> keys(n_voices);
         for (size_t i = 0; i < n_voices; i++) {
             const s2_voice_desc& d = voices[i];
-            Key k;
-            k.kind = d.active ? d.osc_kind : 4u;
-            k.follows = d.mod_env_to_osc_freq != 0.0f ? 2u : d.mod_env_to_lpf_freq != 0.0f ? 1u : 0u;
-            k.mod_rest = k.follows ? d.mod_attack_ms + d.mod_decay_ms : 0.0f;
-            k.amp_rest = d.amp_attack_ms + d.amp_decay_ms;
-            keys[i] = k;
+            keys[i] = {d.active ? d.osc_kind : 4u, d.amp_attack_ms + d.amp_decay_ms};
         }
         std::stable_sort(b->voice_of_slot.begin(), b->voice_of_slot.end(), [&](uint32_t x, uint32_t y) {
             const Key& a = keys[x];
             const Key& c = keys[y];
             if (a.kind != c.kind) return a.kind < c.kind;
-            if (a.follows != c.follows) return a.follows < c.follows;
-            if (a.mod_rest != c.mod_rest) return a.mod_rest < c.mod_rest;
             return a.amp_rest < c.amp_rest;
         });
+        // Deal the sorted warps (32 slots each) round-robin into 8 bins laid out one after the other: every contiguous
+        // eighth / quarter / half of the slot range — the voice ranges of s2_bank_set_pipeline — then holds the same
+        // mix of kinds and envelope lengths, so the ranges' streams advance together.
+        const size_t full_warps = n_voices / 32;
+        if (full_warps >= 16) {
+            std::vector<uint32_t> dealt;
+            dealt.reserve(n_voices);
+            for (size_t bin = 0; bin < 8; bin++)
+                for (size_t w = bin; w < full_warps; w += 8)
+                    dealt.insert(dealt.end(), b->voice_of_slot.begin() + w * 32, b->voice_of_slot.begin() + (w + 1) * 32);
+            dealt.insert(dealt.end(), b->voice_of_slot.begin() + full_warps * 32, b->voice_of_slot.end());
+            b->voice_of_slot.swap(dealt);
+        }
     }
     for (size_t s = 0; s < n_voices; s++) {
         b->slot_of_voice[b->voice_of_slot[s]] = (uint32_t)s;

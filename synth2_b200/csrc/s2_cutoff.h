@@ -89,6 +89,7 @@ S2C_FN float vrcp(float x) {
 // (tools/ubench/fuse_check.cu).  Rule: a packed product never feeds vadd; where the reference adds to a
 // rounded product the add is vaddp(prod, y, one) = fma(prod, 1, y) with the 1 coming from a kernel
 // parameter, which ptxas can neither fold nor fuse (there is no multiply-multiply-add) — same bits as an add.
+#ifndef S2_SCALAR_PAIRS
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) {
     float2 d;
     asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
@@ -110,6 +111,11 @@ __device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) {
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return d;
 }
+#else   // experiment: the same element-wise operations as two scalar instructions (same bits)
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+#endif
 template <> struct Splat<float2> { static __device__ __forceinline__ float2 of(float x) { return make_float2(x, x); } };
 __device__ __forceinline__ float2 vex2(float2 x) { return make_float2(vex2(x.x), vex2(x.y)); }
 __device__ __forceinline__ float2 vrcp(float2 x) { return make_float2(vrcp(x.x), vrcp(x.y)); }
@@ -164,10 +170,25 @@ S2C_FN T exp_neg_fast(T th) {
 // filter needs there, as hi + lo binary32 pairs.  valid = 0: frames of this window take the full evaluation.
 struct Window {
     uint32_t k;             // window index (frame offset >> 5); 0xffffffff = none yet
-    uint32_t valid;
+    uint32_t valid;         // 0: frames of this window take the full evaluation; 1: window evaluation per frame;
+                            // 2: window evaluation at every 4th frame, linear in between (see kInterpRate)
     float thc;              // theta of the centre frame
     float Ah, Al, Bh, Bl;   // sin (A) and cos (B) of thc as hi + lo
+    // scalar form only: the interpolation interval [knode, knode + 4) last evaluated
+    uint32_t knode;
+    float qa, coa, dq, dco;
 };
+
+// Interpolation (second-order filters).  q = (1 - h) / (1 + h), h = damping/2 * sin(theta), and cos(theta) are smooth
+// in the frame offset; the algebra that turns them into (alpha, beta, gamma) is where the reference's rounding lives
+// (alpha = (1/2 + beta - gamma) / 4 cancels).  So q and cos are evaluated through the window at the frames of an
+// absolute grid of 4 and taken linear in between, and the coefficient algebra runs per frame on them exactly as the
+// reference's does.  Linear interpolation of cos over an interval of d radians is off by at most d^2 / 8; with the
+// angle moving by the factor 2^(amt * es) per frame, d = 4 ln2 |amt es| theta, which makes the relative error of
+// alpha (~theta^2 / 4 at low cutoffs, the sensitive end) (4 ln2 |amt es|)^2 / 2: 9e-8 for the bench bank's sweep
+// (1.5 octaves in 200 ms), 4.2e-6 for the default patch's (10 octaves in 200 ms) — against the 2e-4 by which the
+// reference's own binary32 alpha scatters from frame to frame at 100 Hz.  Faster sweeps evaluate every frame.
+constexpr float kInterpRate12 = 0.0135f;      // 12 |amt es| <= this
 
 S2C_FN void split_hi_lo(double v, float* hi, float* lo) {
     *hi = (float)v;
@@ -186,24 +207,43 @@ S2C_FN void window_sincos(const Window& W, T d, T* s, T* c) {
     *c = vadd(splat<T>(W.Bh), vadd(splat<T>(W.Bl), cc));
 }
 
-// Second-order low-pass / high-pass coefficients from sin and cos (dsp_filters.rs:99-109, :149-159), with the
-// output doubling folded in: c0 = 2 alpha, c1 = 2 beta, c2 = 2 gamma.  Callers guarantee 1 <= 1 + h <= 9 (a valid
-// window: 0 < theta < pi and 0 <= hd <= 8); anything else goes through biquad_lp_hp_any below.  Scaling by a power of two commutes with
-// round-to-nearest, so with q = RN(num / den): 2 beta = q, 1/2 + beta = RN(1 + q) / 2, 2 gamma = RN(RN(1 + q) cos),
-// 2 alpha = RN(RN(1 + q) -+ 2 gamma) / 4 — the reference's roundings, fewer operations.  hd = damping / 2.
-template <bool HIGH_PASS, class T>
-S2C_FN void biquad_lp_hp(T s, T co, float hd, float one, T* c0, T* c1, T* c2) {
+// q = (1 - h) / (1 + h), h = hd * sin (dsp_filters.rs:108 / :158 with beta = q / 2), for 1 <= 1 + h <= 9
+template <class T>
+S2C_FN T quotient_of(T s, float hd, float one) {
     const T h = vmul(splat<T>(hd), s);
     const T num = vfma(h, splat<T>(-one), splat<T>(1.0f));               // 1 - h, one rounding (exact product)
     const T den = vfma(h, splat<T>(one), splat<T>(1.0f));                // 1 + h
     const T nden = vfma(h, splat<T>(-one), splat<T>(-1.0f));             // -(1 + h): the same rounding, mirrored
-    const T q = div_in_range(num, den, nden);
+    return div_in_range(num, den, nden);
+}
+
+// Second-order low-pass / high-pass coefficients from q and cos (dsp_filters.rs:99-109, :149-159), with the output
+// doubling folded in: c0 = 2 alpha, c1 = 2 beta, c2 = 2 gamma.  Scaling by a power of two commutes with
+// round-to-nearest, so with q = 2 beta: 1/2 + beta = RN(1 + q) / 2, 2 gamma = RN(RN(1 + q) cos),
+// 2 alpha = RN(RN(1 + q) -+ 2 gamma) / 4 — the reference's roundings, fewer operations.
+template <bool HIGH_PASS, class T>
+S2C_FN void biquad_from_q_cos(T q, T co, float one, T* c0, T* c1, T* c2) {
     const T hb2 = vadd(q, splat<T>(1.0f));
     const T g2 = vmul(hb2, co);
     const T t = vfma(g2, splat<T>(HIGH_PASS ? one : -one), hb2);           // RN(hb2 -+ g2)
     *c0 = vmul(t, splat<T>(0.25f));
     *c1 = q;
     *c2 = g2;
+}
+
+// From sin and cos.  Callers guarantee 1 <= 1 + h <= 9 (a valid window: 0 < theta < pi and 0 <= hd <= 8); anything
+// else goes through biquad_lp_hp_any below.  hd = damping / 2.
+template <bool HIGH_PASS, class T>
+S2C_FN void biquad_lp_hp(T s, T co, float hd, float one, T* c0, T* c1, T* c2) {
+    biquad_from_q_cos<HIGH_PASS, T>(quotient_of<T>(s, hd, one), co, one, c0, c1, c2);
+}
+
+// (q, cos) of the frame(s) whose mod-envelope value is m, through window W
+template <class T>
+S2C_FN void node_q_cos(const Window& W, T m, float amount, float theta0, float hd, float one, T* q, T* co) {
+    T s;
+    window_sincos<T>(W, delta_at<T>(m, amount, theta0, W.thc), &s, co);
+    *q = quotient_of<T>(s, hd, one);
 }
 
 // The same coefficients for any operands (frames outside valid windows): inside the straight-line division's

@@ -49,6 +49,7 @@ struct OscC {                // everything derived from the period; hoisting a d
 
 struct FiltC {               // one-pole: c0 = k, c1 = 1 - k.   biquad: c0 = 2*alpha, c1 = 2*beta, c2 = 2*gamma
     float c0, c1, c2;
+    float co;                // second-order low-pass / high-pass: cos(theta) the coefficients were made from (resting only)
     uint32_t fl_bits;
 };
 
@@ -210,6 +211,7 @@ __device__ __forceinline__ void make_filt_theta(FiltC& c, float th, float damp) 
         c.c0 = __fmul_rn(2.0f, alpha);
         c.c1 = __fmul_rn(2.0f, beta);
         c.c2 = __fmul_rn(2.0f, gamma);
+        c.co = co;
     } else if (FILTER == FILT_BIQUAD_BP) {
         // try3/dsp_filters.rs:197-207; `damp` carries the quality factor
         const float tn = s2_tanf(__fdiv_rn(th, __fmul_rn(2.0f, damp)));
@@ -247,7 +249,9 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         c.c0 = k;
         c.c1 = __fsub_rn(1.0f, k);
         c.c2 = 0.0f;
+        c.co = 0.0f;
     } else {
+        c.co = 0.0f;
         make_filt_theta<FILTER>(c, theta_ref(fl, sr), damp);
     }
 }
@@ -274,7 +278,7 @@ __device__ __forceinline__ CutP make_cutp(float lpf, float amt_lpf, float damp, 
 // 2^-7 (theta changes by the factor 2^(amt * es) per frame: |d| <= thc * 16 ln 2 |amt es| (1 + ...) < thc * 12 |amt es|)
 // and the damping suits the straight-line division.  A pure function of (voice, n >> 5).
 template <int FILTER>
-__device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
+__device__ __forceinline__ void make_window_inl(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
     const uint32_t k = n >> s2c::kWinShift;
     W.k = k;
     const uint32_t w0 = k << s2c::kWinShift;
@@ -285,8 +289,10 @@ __device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const
                  __fmul_rn(thc, r12) <= s2c::kWinDelta;
     if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) valid = valid && cp.hd >= 0.0f && cp.hd <= 8.0f;
     if (FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_BP) valid = false;      // these never look at a window
-    W.valid = valid ? 1u : 0u;
+    W.valid = !valid ? 0u : ((FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) && r12 <= s2c::kInterpRate12) ? 2u : 1u;
     W.thc = thc;
+    W.knode = 0xffffffffu;
+    W.qa = W.coa = W.dq = W.dco = 0.0f;
     if (valid) {
         double sd, cd;
         s2_sincos_d((double)thc, &sd, &cd);
@@ -295,6 +301,16 @@ __device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const
     } else {
         W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
     }
+}
+
+__device__ __forceinline__ void window_none(s2c::Window& W) {
+    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    W.knode = 0xffffffffu; W.qa = W.coa = W.dq = W.dco = 0.0f;
+}
+
+template <int FILTER>
+__device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
+    make_window_inl<FILTER>(W, sm, cp, n);
 }
 
 // Coefficients of one moving frame (scalar form): m = the mod envelope at frame n (inside segment sm).
@@ -311,7 +327,21 @@ __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const Seg
     }
     if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp); return; }
     if ((n >> s2c::kWinShift) != W.k) make_window<FILTER>(W, sm, cp, n);
-    if (W.valid) {
+    if (W.valid == 2u && (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP)) {
+        // q and cos at the frames of the absolute grid of 4 around n, linear in between (s2_cutoff.h)
+        const uint32_t k = n & ~3u;
+        if (k != W.knode) {
+            float qb, cob;
+            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k)), cp.amt, cp.theta0, cp.hd, one, &W.qa, &W.coa);
+            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k + 4u)), cp.amt, cp.theta0, cp.hd, one, &qb, &cob);
+            W.dq = __fmul_rn(__fsub_rn(qb, W.qa), 0.25f);
+            W.dco = __fmul_rn(__fsub_rn(cob, W.coa), 0.25f);
+            W.knode = k;
+        }
+        const float j = __uint2float_rn(n & 3u);
+        s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float>(__fmaf_rn(j, W.dq, W.qa), __fmaf_rn(j, W.dco, W.coa), one,
+                                                                &c.c0, &c.c1, &c.c2);
+    } else if (W.valid) {
         float s, co;
         s2c::window_sincos<float>(W, s2c::delta_at<float>(m, cp.amt, cp.theta0, W.thc), &s, &co);
         if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
@@ -338,6 +368,25 @@ __device__ __forceinline__ bool stage_moves(int stage) { return stage == 0 || st
 // scalar-tail envelope (env_scalar) needs the full EnvP.
 struct EnvQ { float A, AD, S, Rs, E, sA, sD, sR; };
 __device__ __forceinline__ EnvQ compact(const EnvP& e) { return {e.A, e.AD, e.S, e.Rs, e.E, e.sA, e.sD, e.sR}; }
+
+// Decode one voice's parameter column (struct-of-arrays, see s2_internal.h).
+__device__ __forceinline__ Lane load_lane(const float* __restrict__ P, uint32_t vp, float sr) {
+    Lane L;
+    L.kind = __float_as_uint(P[P_KIND * vp]);
+    const uint32_t seed = __float_as_uint(P[P_SEED * vp]);
+    L.rot = (seed << 5) | (seed >> 27);
+    L.pitch = P[P_PITCH * vp];
+    L.gain = P[P_GAIN * vp];
+    L.namt = P[P_NOISE * vp];
+    L.lpf = P[P_LPF * vp];
+    L.damp = P[P_DAMP * vp];
+    L.amt_osc = P[P_AMT_OSC * vp];
+    L.amt_lpf = P[P_AMT_LPF * vp];
+    const uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
+    make_env(L.amp, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
+    make_env(L.mod, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
+    return L;
+}
 
 // ------------------------------------------------------------------------------------------
 // One frame of one voice.
@@ -492,6 +541,17 @@ enum { G_CONST = 0,      // every frame of the chunk lies in a segment of slope 
        G_LINE = 1,       // every frame lies in the lane's current segment: one line, two frames per instruction
        G_ANY = 2 };      // a stage boundary falls inside the chunk for some lane: per pair, the full stage chain at boundaries
 
+// The amp envelope of frames (x, x + 1) where a stage boundary falls on or between them: the full stage chain for
+// both, then the segment of the frame after them.  Out of line: it runs a handful of times per voice per render.
+struct AmpEdge { float2 g; SegEnv sg; };
+static __device__ __noinline__ AmpEdge amp_at_boundary(const EnvQ* __restrict__ amp, float xa, float xb, uint32_t n_next) {
+    const EnvQ A = *amp;
+    AmpEdge e;
+    e.g = make_float2(env_x16(A, xa), env_x16(A, xb));
+    e.sg = seg_env(A, n_next);
+    return e;
+}
+
 // Waveform of frames (i, i + 1) from their phases, period constant (the `% period` is a no-op, see osc_step).
 template <int KIND>
 __device__ __forceinline__ float2 wave2(const FastV& F, float2 ph2, float hbig, uint32_t kind, const float* sintab) {
@@ -558,7 +618,7 @@ __device__ __forceinline__ float2 input2(const FastV& F, float2 osc2, uint32_t h
 // 2^27 rotate to multiples of 32), so (seed' ^ (offset + i)) == (seed' ^ offset) + i and the hash of frame i is one
 // add with an immediate.
 template <int FILTER, int KIND, int GMODE, bool FASTHASH, int TRACE>
-__device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvP* __restrict__ amp, float one, uint32_t kind, uint32_t rot,
+__device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvQ* __restrict__ amp, float one, uint32_t kind, uint32_t rot,
                                               uint32_t n0, float* __restrict__ row, const float* sintab) {
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);               // (P / 2) * 2^60, exact
     uint32_t n = n0;
@@ -567,7 +627,7 @@ __device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvP* __restrict__
     if (GMODE == G_ANY) sg = seg_env(*amp, n0);
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
-    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.co = 0.0f; fc.fl_bits = 0;
     float ph = F.ph;
     // 8 frames per trip: long enough to overlap neighbouring frames, short enough for the instruction cache
 #pragma unroll 1
@@ -608,10 +668,9 @@ __device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvP* __restrict__
                     g2.x = seg_eval(sg, xf2.x);
                     g2.y = seg_eval(sg, xf2.y);
                 } else {
-                    // a stage boundary: the full stage chain for these two frames, then the next segment
-                    g2.x = env_x16(*amp, xf2.x);
-                    g2.y = env_x16(*amp, xf2.y);
-                    sg = seg_env(*amp, ne + 2u);
+                    const AmpEdge e = amp_at_boundary(amp, xf2.x, xf2.y, ne + 2u);
+                    g2 = e.g;
+                    sg = e.sg;
                 }
                 xf2 = padd2(xf2, splat2(2.0f));
             }
@@ -632,74 +691,109 @@ struct MovV {
     CutP cp;
     float mes, mnex0, mey0;      // the mod envelope's segment line (the whole chunk lies inside it)
     bool moving;                 // false: this lane's cutoff rests (F.c0 .. F.c2) while others of the warp move
+    float q_rest, co_rest;       // a resting lane's 2 beta and cos(theta): interpolation nodes that never move
 };
 
 // Moving-cutoff chunk, packed: the period is constant but the mod envelope is in a ramp, so the cutoff — and with
 // it the filter coefficients — changes every frame (process.rs:148-152, 363-371; the first 200 ms of every note of
-// the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every active lane): the
+// the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every moving lane): the
 // chunk starts at a multiple of 32 frames, lies inside one segment of the mod envelope, and (second-order
-// filters) its window W is valid.  Coefficients of frames (i, i + 1) in packed arithmetic (s2_cutoff.h), the amp
-// envelope per pair as in G_ANY.  MIXED: some lanes' cutoffs rest; they select their constants.
-template <int FILTER, int KIND, bool MIXED, int TRACE>
-__device__ __forceinline__ void chunk_modcut_pk(FastV& F, const EnvP* __restrict__ amp, const MovV& mv, const s2c::Window& W,
+// filters) its window W is valid — at level 2 for INTERP (q and cos at every 4th frame, linear in between), at
+// level 1 otherwise (every frame); the chunk also lies inside the lane's current amp-envelope segment (F.es ..,
+// as G_LINE).  Everything in packed arithmetic on frames (i, i + 1) (s2_cutoff.h).  MIXED: some lanes' cutoffs rest;
+// they select their constants.
+template <int FILTER, int KIND, bool MIXED, bool INTERP, bool FASTHASH, int TRACE>
+__device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const s2c::Window& W,
                                                 float one, uint32_t kind, uint32_t rot, uint32_t n0,
                                                 float* __restrict__ row, const float* sintab) {
     static_assert(FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
+    static_assert(!INTERP || FILTER != FILT_ONE_POLE, "the one-pole evaluates every frame");
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
     uint32_t n = n0;
     float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
-    SegEnv sg = seg_env(*amp, n0);
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     float ph = F.ph;
-#pragma unroll 1
-    for (int j = 0; j < kChunk / 4; j++) {
-        float o4[4];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            // ---- coefficients of the two frames
-            const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
-            float2 c0, c1, c2;
-            if (FILTER == FILT_ONE_POLE) {
-                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
-                c1 = pfma2(c0, splat2(-one), splat2(1.0f));           // 1 - k, one rounding (exact product)
-                c2 = splat2(0.0f);
-            } else {
-                float2 s2v, co2;
-                s2c::window_sincos<float2>(W, s2c::delta_at<float2>(m2, mv.cp.amt, mv.cp.theta0, W.thc), &s2v, &co2);
-                s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2v, co2, mv.cp.hd, one, &c0, &c1, &c2);
-            }
-            FiltC ca, cb;
-            if (MIXED && !mv.moving) {
-                ca.c0 = cb.c0 = F.c0; ca.c1 = cb.c1 = F.c1; ca.c2 = cb.c2 = F.c2;
-            } else {
-                ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
-                cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
-            }
-            // ---- oscillator, noise, filter
-            const float pa = ph;
-            const float pb = wrap_unit(__fadd_rn(pa, F.d));
-            ph = wrap_unit(__fadd_rn(pb, F.d));
-            const float2 ph2 = make_float2(pa, pb);
-            const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
-            const uint32_t ha = (rot ^ n) * 0x9e3779b9u, hb = (rot ^ (n + 1u)) * 0x9e3779b9u;
-            const float2 u2 = input2<false>(F, osc2, ha, hb);
-            const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
-            // ---- amp envelope
-            float2 g2;
-            if (n + 2u <= sg.nend) {
-                g2 = s2c::vaddp(pmul2(splat2(sg.es), padd2(xf2, splat2(sg.nex0))), splat2(sg.ey0), one);
-            } else {
-                g2.x = env_x16(*amp, xf2.x);
-                g2.y = env_x16(*amp, xf2.y);
-                sg = seg_env(*amp, n + 2u);
-            }
-            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
-            o4[2 * h] = out2.x;
-            o4[2 * h + 1] = out2.y;
-            n += 2u;
-            xf2 = padd2(xf2, splat2(2.0f));
+    uint32_t nbc = 0;                 // FASTHASH: hash of the trip's first frame (see chunk_fast_tp)
+    auto mod2 = [&](float2 x2) {      // the mod envelope's line at two frame offsets
+        return s2c::vaddp(pmul2(splat2(mv.mes), padd2(x2, splat2(mv.mnex0))), splat2(mv.mey0), one);
+    };
+    // one pair of frames with coefficients (c0, c1, c2) per frame; fi = index of the pair's first frame in its trip
+    auto pair = [&](float2 c0, float2 c1, float2 c2, uint32_t fi, float* o2) {
+        FiltC ca, cb;
+        if (MIXED && !mv.moving) {
+            ca.c0 = cb.c0 = F.c0; ca.c1 = cb.c1 = F.c1; ca.c2 = cb.c2 = F.c2;
+        } else {
+            ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
+            cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
         }
-        *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        const float pa = ph;
+        const float pb = wrap_unit(__fadd_rn(pa, F.d));
+        ph = wrap_unit(__fadd_rn(pb, F.d));
+        const float2 ph2 = make_float2(pa, pb);
+        const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
+        const uint32_t ha = FASTHASH ? nbc + fi * 0x9e3779b9u : (rot ^ n) * 0x9e3779b9u;
+        const uint32_t hb = FASTHASH ? nbc + (fi + 1u) * 0x9e3779b9u : (rot ^ (n + 1u)) * 0x9e3779b9u;
+        const float2 u2 = input2<FASTHASH>(F, osc2, ha, hb);
+        const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
+        const float2 g2 = s2c::vaddp(pmul2(splat2(F.es), padd2(xf2, splat2(F.nex0))), splat2(F.ey0), one);
+        const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
+        o2[0] = out2.x;
+        o2[1] = out2.y;
+        n += 2u;
+        xf2 = padd2(xf2, splat2(2.0f));
+    };
+    if constexpr (INTERP) {
+        // nodes n0, n0 + 4 now; inside the loop the next two, one 8-frame trip ahead.  A resting lane's nodes are its
+        // own 2 beta and cos(theta): the same algebra then reproduces its resting coefficients bit for bit (make_filt).
+        float2 qA, coA;
+        s2c::node_q_cos<float2>(W, mod2(padd2(splat2(xf2.x), make_float2(0.0f, 4.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, &qA, &coA);
+        if (!mv.moving) { qA = splat2(mv.q_rest); coA = splat2(mv.co_rest); }
+#pragma unroll 1
+        for (int jt = 0; jt < kChunk / 8; jt++) {
+            if (FASTHASH) nbc = (rot ^ n) * 0x9e3779b9u;
+            float2 qB, coB;
+            s2c::node_q_cos<float2>(W, mod2(padd2(splat2(xf2.x), make_float2(8.0f, 12.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, &qB, &coB);
+            if (!mv.moving) { qB = qA; coB = coA; }
+#pragma unroll
+            for (int sgi = 0; sgi < 2; sgi++) {
+                const float qa = sgi ? qA.y : qA.x, qb = sgi ? qB.x : qA.y;
+                const float ca = sgi ? coA.y : coA.x, cb = sgi ? coB.x : coA.y;
+                const float dq = __fmul_rn(__fsub_rn(qb, qa), 0.25f), dco = __fmul_rn(__fsub_rn(cb, ca), 0.25f);
+                float o4[4];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
+                    float2 c0, c1, c2;
+                    s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(qa)), pfma2(j2, splat2(dco), splat2(ca)),
+                                                                             one, &c0, &c1, &c2);
+                    pair(c0, c1, c2, 4u * sgi + 2u * h, o4 + 2 * h);
+                }
+                *reinterpret_cast<float4*>(row + 8 * jt + 4 * sgi) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+            qA = qB; coA = coB;
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < kChunk / 4; j++) {
+            if (FASTHASH && (j & 1) == 0) nbc = (rot ^ n) * 0x9e3779b9u;
+            float o4[4];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float2 m2 = mod2(xf2);
+                float2 c0, c1, c2;
+                if (FILTER == FILT_ONE_POLE) {
+                    c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
+                    c1 = pfma2(c0, splat2(-one), splat2(1.0f));           // 1 - k, one rounding (exact product)
+                    c2 = splat2(0.0f);
+                } else {
+                    float2 s2v, co2;
+                    s2c::window_sincos<float2>(W, s2c::delta_at<float2>(m2, mv.cp.amt, mv.cp.theta0, W.thc), &s2v, &co2);
+                    s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2v, co2, mv.cp.hd, one, &c0, &c1, &c2);
+                }
+                pair(c0, c1, c2, 4u * (j & 1) + 2u * h, o4 + 2 * h);
+            }
+            *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
     }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
@@ -712,7 +806,7 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const EnvP* __restrict
 // envelope and frame offset — a detune / pitch sweep of one patch, BASELINE config 5), so the 32 frames'
 // coefficients were computed once, one frame per lane, into `ctab` ([c0 | c1 | c2][32], see modcut_coefficients).
 template <int FILTER, int KIND, int TRACE, bool SHARED>
-__device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvP* __restrict__ amp, const MovV& mv, const SegEnv& sm,
+__device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvQ* __restrict__ amp, const MovV& mv, const SegEnv& sm,
                                                 float one, uint32_t kind, uint32_t rot, uint32_t n0,
                                                 float* __restrict__ row, const float* sintab, const float* __restrict__ ctab) {
     SegEnv sa = seg_env(*amp, n0);
@@ -720,9 +814,9 @@ __device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvP* __restrict
     o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
-    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.co = 0.0f; fc.fl_bits = 0;
     s2c::Window W;
-    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    window_none(W);
     float ph = F.ph;
     uint32_t n = n0;
     float xf = __uint2float_rn(n0);                               // exact: n0 + 32 <= 2^24
@@ -751,7 +845,7 @@ __device__ __forceinline__ void modcut_coefficients(const SegEnv& sm, const CutP
                                                     float* __restrict__ ctab) {
     const uint32_t n = n0 + (uint32_t)lane;
     s2c::Window W;
-    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    window_none(W);
     FiltC c;
     moving_coefs<FILTER>(c, W, sm, cp, one, n, seg_eval(sm, __uint2float_rn(n)));
     ctab[lane] = c.c0; ctab[32 + lane] = c.c1; ctab[64 + lane] = c.c2;
@@ -766,7 +860,7 @@ struct MovG {
 __device__ __forceinline__ void movg_init(MovG& g, float lpf, float amt_lpf, float damp, float sr) {
     g.cp = make_cutp(lpf, amt_lpf, damp, sr);
     g.sm.nbeg = 1u; g.sm.nend = 0u; g.sm.es = g.sm.nex0 = g.sm.ey0 = 0.0f; g.sm.stage = 4;
-    g.W.k = 0xffffffffu; g.W.valid = 0u; g.W.thc = 0.0f; g.W.Ah = g.W.Al = g.W.Bh = g.W.Bl = 0.0f;
+    window_none(g.W);
 }
 
 // Filter coefficients of x16 frame n (m = its mod-envelope value): the moving evaluation while the mod envelope ramps
@@ -821,11 +915,12 @@ __device__ __forceinline__ float general_frame(const Lane& L, float sr, float on
 // register budget that keeps all 13.8 warps per SM resident.  An odd word count keeps the 32
 // lanes of a warp on distinct banks.
 struct Cold {
-    Lane L;
+    EnvQ amp, mod;         // the envelopes as the x16 path evaluates them (the scalar tail re-derives the full form)
+    float pitch, lpf, damp, amt_osc, amt_lpf;
+    float theta0;          // (2 pi cutoff) / sr
     OscC oc;
     FiltC fc;
     SegEnv msg;            // the mod-envelope ramp the voice's moving cutoff is in (flags bit 2)
-    float theta0;          // (2 pi cutoff) / sr
     uint32_t n_safe;       // the resting constants (period, cutoff) are valid for frame offsets [.., n_safe)
     uint32_t vi;           // slot index (state/params column)
     uint32_t out_row;      // caller-visible voice index, 0xffffffff = no such voice
@@ -836,7 +931,7 @@ constexpr int kRowPtrWords = 2;    // one 64-bit output-row base per tile row (0
 constexpr int kCoefWords = 96;     // shared moving-cutoff coefficients of one chunk: [c0 | c1 | c2][32]
 
 __host__ __device__ constexpr size_t warp_smem_floats() {
-    return 32 * kTileStride + 32 * kColdWords + 32 * kRowPtrWords + kCoefWords;
+    return 32 * kTileStride + 32 * kColdWords + 32 * kRowPtrWords + kCoefWords;      // 14.8 KB: 14 one-warp blocks per SM
 }
 
 }  // namespace s2

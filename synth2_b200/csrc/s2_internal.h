@@ -27,7 +27,7 @@ enum StateIdx {
     // exp / sin / cos in binary64), keyed by the exact input bits: a launch that finds its key reuses
     // them instead of re-deriving ~1000 instructions per voice.  Not part of s2_voice_state.
     S_FO_KEY, S_OSC_P, S_OSC_D, S_OSC_SLOPE, S_OSC_HALF, S_OSC_TS1, S_OSC_TS2,
-    S_FL_KEY, S_DAMP_KEY, S_FC_C0, S_FC_C1, S_FC_C2,
+    S_FL_KEY, S_DAMP_KEY, S_FC_C0, S_FC_C1, S_FC_C2, S_FC_CO,
     S_COUNT
 };
 constexpr uint32_t kNoKey = 0x7fc00001u;   // a NaN payload no frequency can have
@@ -53,8 +53,13 @@ struct RenderArgs {
 };
 
 constexpr int kWarpsPerBlock = 1;
-constexpr int kChunk = 32;          // frames per warp tile
-constexpr int kTileStride = 36;     // floats per tile row: 16-B aligned rows, conflict-free STS.128/LDS.128
+constexpr int kChunk = 32;          // frames per compute chunk (classification granularity)
+// The render kernel's tile is 32 voices x 64 frames = two chunks: a warp then writes 256 contiguous bytes per output
+// row per visit.  128 bytes per row per visit tops out at 5.1 TB/s of write bandwidth on this part whatever the
+// kernel does in between, 256 bytes at 5.9 TB/s (tools/ubench/write_bw.cu, profiles/r2_write_bw.txt).
+constexpr int kTileFrames = 64;
+constexpr int kTileStride = 68;     // floats per tile row: 16-B aligned rows, conflict-free STS.128/LDS.128
+constexpr int kTsTileStride = 36;   // the time-split kernel's 32-frame tile
 
 // Launchers (s2_kernels.cu).  Return the cudaError_t of the launch.  A warp renders 32 consecutive slots.
 cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, cudaStream_t stream);

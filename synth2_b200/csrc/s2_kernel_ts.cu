@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32) ts_phase_kernel(const RenderArgs a, float*
 }
 
 template <int FILTER, bool GCONST>
-__device__ __forceinline__ void ts_chunk_kind(FastV& F, const EnvP* amp, float one, uint32_t kind, uint32_t rot, uint32_t n,
+__device__ __forceinline__ void ts_chunk_kind(FastV& F, const EnvQ* amp, float one, uint32_t kind, uint32_t rot, uint32_t n,
                                               float* row, const float* sintab) {
     constexpr int G = GCONST ? G_CONST : G_ANY;
     switch (kind) {                       // warp-uniform: a warp is one voice
@@ -105,7 +105,7 @@ __device__ __forceinline__ void ts_moving_sweep(const EnvP& A, const EnvP& M, fl
                                                 M22& mprod, float* tile, int lane, float* __restrict__ gout,
                                                 const float* sintab) {
     const int q = lane >> 3, c4 = (lane & 7) * 4;
-    float* row = tile + lane * kTileStride;
+    float* row = tile + lane * kTsTileStride;
     SegEnv sa = seg_env(A, nl);
     uint32_t n = nl;
     float xf = __uint2float_rn(nl);
@@ -143,7 +143,7 @@ __device__ __forceinline__ void ts_moving_sweep(const EnvP& A, const EnvP& M, fl
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int r = 4 * i + q;                      // tile row = segment r
-                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTsTileStride + c4);
                 __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
             }
             __syncwarp();
@@ -155,8 +155,8 @@ __device__ __forceinline__ void ts_moving_sweep(const EnvP& A, const EnvP& M, fl
 template <int FILTER, bool MOVING>
 __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const float* __restrict__ seg_phase) {
     extern __shared__ __align__(16) float smem[];
-    float* tile = smem;                                      // [32 segments][kTileStride]
-    float* sintab = smem + 32 * kTileStride;
+    float* tile = smem;                                      // [32 segments][kTsTileStride]
+    float* sintab = smem + 32 * kTsTileStride;
     const int lane = threadIdx.x;
     const uint32_t slot = blockIdx.x;
     const uint32_t vp = a.vpad;
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     EnvP A, M;
     make_env(A, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
     make_env(M, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
+    const EnvQ Aq = compact(A);
     float* __restrict__ S = a.state + slot;
     const uint32_t n0 = __float_as_uint(S[S_OFFSET * vp]);
 
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     const float* __restrict__ sp = seg_phase + (size_t)slot * (3 * kSegs);
     const float ph0 = sp[lane];
     const uint32_t nl = n0 + (uint32_t)lane * L;             // this lane's first frame offset
-    float* row = tile + lane * kTileStride;
+    float* row = tile + lane * kTsTileStride;
     __syncwarp();
 
     // delayed inputs of the biquad at the segment start: carried state for segment 0, otherwise the
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
     } else {
         F.ph = ph0;
         F.x1 = x1_in; F.x2 = x2_in; F.y1 = 0.0f; F.y2 = 0.0f;
-        for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &A, a.one, kind, rot, nl + c, row, sintab);
+        for (uint32_t c = 0; c < L; c += kChunk) ts_chunk_kind<FILTER, true>(F, &Aq, a.one, kind, rot, nl + c, row, sintab);
     }
 
     // ---- the segment maps compose left to right: inclusive Hillis-Steele scan over the lanes
@@ -295,12 +296,12 @@ __global__ void __launch_bounds__(32) ts_render_kernel(const RenderArgs a, const
         F.ph = ph0;
         F.x1 = x1_in; F.x2 = x2_in; F.y1 = y1_in; F.y2 = y2_in;
         for (uint32_t c = 0; c < L; c += kChunk) {
-            ts_chunk_kind<FILTER, false>(F, &A, a.one, kind, rot, nl + c, row, sintab);
+            ts_chunk_kind<FILTER, false>(F, &Aq, a.one, kind, rot, nl + c, row, sintab);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int r = 4 * i + q;                      // tile row = segment r
-                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+                const float4 val = *reinterpret_cast<const float4*>(tile + r * kTsTileStride + c4);
                 __stcs(reinterpret_cast<float4*>(gout + (size_t)r * L + c + c4), val);
             }
             __syncwarp();
@@ -324,7 +325,7 @@ cudaError_t launch_ts_phase(const RenderArgs& a, float* seg_phase, cudaStream_t 
 cudaError_t launch_ts_render(const RenderArgs& a, uint32_t filter_kind, bool moving, const float* seg_phase,
                              cudaStream_t stream) {
     if (a.n_voices == 0) return cudaSuccess;
-    const size_t smem = (32 * kTileStride + 1024) * sizeof(float);
+    const size_t smem = (32 * kTsTileStride + 1024) * sizeof(float);
     if (filter_kind == 0) {
         if (moving) ts_render_kernel<0, true><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);
         else ts_render_kernel<0, false><<<a.n_voices, 32, smem, stream>>>(a, seg_phase);

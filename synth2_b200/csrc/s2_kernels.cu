@@ -12,6 +12,8 @@
 // Reference line numbers are relative to /root/reference/components/s2_lib/src/.
 #include "s2_device.cuh"
 
+#include <type_traits>
+
 // Register cap of the render kernel, as a minimum of resident one-warp blocks per SM: 20 blocks = 65,536 / (20 * 32)
 // = 102 -> 96 registers.  96 keeps the fast loops spill-free and lets 16+ one-warp blocks share an SM, so blocks of
 // overlapping launches (pipelined mode) find room: measured 1.079e12 voice-samples/s at 96 against 1.047e12 at 128
@@ -41,7 +43,7 @@ __device__ __forceinline__ void tree_sum_rows(float4 (&val)[N], float2& b01, flo
 
 // One fast tile of a kind-uniform (or mixed, KIND = -1) warp, by envelope mode and hash form.
 template <int FILTER, int KIND, int TRACE>
-__device__ __forceinline__ void fast_tile(int gmode, bool fasthash, FastV& F, const EnvP* amp, float one, uint32_t kind,
+__device__ __forceinline__ void fast_tile(int gmode, bool fasthash, FastV& F, const EnvQ* amp, float one, uint32_t kind,
                                           uint32_t rot, uint32_t n, float* row, const float* sintab) {
     // the steady states (sustain / tail, straight ramps) of banks without added noise get the specialised loops;
     // added noise amounts, odd offsets and chunks with a stage boundary share the general variant
@@ -89,21 +91,12 @@ render_kernel(const RenderArgs a) {
         active = exists && __float_as_uint(P[P_ACTIVE * vp]) != 0u;
         C.vi = vi;
         C.out_row = exists ? __float_as_uint(P[P_ROW * vp]) : 0xffffffffu;
-        Lane L;
-        L.kind = kind = __float_as_uint(P[P_KIND * vp]);
-        const uint32_t seed = __float_as_uint(P[P_SEED * vp]);
-        L.rot = rot = (seed << 5) | (seed >> 27);
-        L.pitch = P[P_PITCH * vp];
-        L.gain = P[P_GAIN * vp];
-        L.namt = P[P_NOISE * vp];
-        L.lpf = P[P_LPF * vp];
-        L.damp = P[P_DAMP * vp];
-        L.amt_osc = P[P_AMT_OSC * vp];
-        L.amt_lpf = P[P_AMT_LPF * vp];
-        const uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
-        make_env(L.amp, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
-        make_env(L.mod, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
-        C.L = L;
+        const Lane L = load_lane(P, vp, sr);
+        kind = L.kind;
+        rot = L.rot;
+        C.amp = compact(L.amp);
+        C.mod = compact(L.mod);
+        C.pitch = L.pitch; C.lpf = L.lpf; C.damp = L.damp; C.amt_osc = L.amt_osc; C.amt_lpf = L.amt_lpf;
         C.flags = (active ? 1u : 0u) | ((L.amt_osc != 0.0f || L.amt_lpf != 0.0f) ? 2u : 0u);
         C.theta0 = theta_ref(L.lpf, sr);
 
@@ -126,10 +119,10 @@ render_kernel(const RenderArgs a) {
         C.oc = oc;
         FiltC fc;
         fc.fl_bits = __float_as_uint(S[S_DAMP_KEY * vp]) == __float_as_uint(L.damp) ? __float_as_uint(S[S_FL_KEY * vp]) : kNoKey;
-        fc.c0 = S[S_FC_C0 * vp]; fc.c1 = S[S_FC_C1 * vp]; fc.c2 = S[S_FC_C2 * vp];
+        fc.c0 = S[S_FC_C0 * vp]; fc.c1 = S[S_FC_C1 * vp]; fc.c2 = S[S_FC_C2 * vp]; fc.co = S[S_FC_CO * vp];
         C.fc = fc;
         C.n_safe = 0u;
-        C.msg.nbeg = 1u; C.msg.nend = 0u;
+        C.msg.es = C.msg.nex0 = C.msg.ey0 = 0.0f; C.msg.nbeg = 1u; C.msg.nend = 0u; C.msg.stage = 4;
         F.P = 0.0f; F.d = 0.0f; F.slope = 0.0f; F.nhalf = 0.0f; F.ts1 = 0.0f; F.ts2 = 0.0f;
         F.c0 = 0.0f; F.c1 = 0.0f; F.c2 = 0.0f;
         F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 0.0f;
@@ -155,8 +148,8 @@ render_kernel(const RenderArgs a) {
     // per lane (modcut_coefficients).  Offsets advance together, so this holds for the launch.
     bool filt_uniform = false;
     {
-        const EnvP& M = C.L.mod;
-        const float key[10] = {C.L.lpf, C.L.damp, C.L.amt_lpf, M.A, M.AD, M.S, M.Rs, M.E, M.sD, M.sR};
+        const EnvQ& M = C.mod;
+        const float key[10] = {C.lpf, C.damp, C.amt_lpf, M.A, M.AD, M.S, M.Rs, M.E, M.sD, M.sR};
         // (every lane must execute every shuffle: no short-circuit between them)
         const uint32_t n_lead = __shfl_sync(0xffffffffu, n, leader);
         const float sa_lead = __shfl_sync(0xffffffffu, M.sA, leader);
@@ -172,12 +165,12 @@ render_kernel(const RenderArgs a) {
     const uint32_t f16 = frames & ~15u;            // x16 region (process.rs:26-37), then the scalar tail
     const size_t stride = a.row_stride;
     float* __restrict__ gout = a.voice_out;
-    // Output rows are indexed by the caller's voice index, which the bank may have permuted into
-    // kind-uniform warps (P_ROW).  Transposed write-back: lanes 8q..8q+7 cover 128 contiguous bytes of
-    // tile row 4*i + q, so each STG.128 of the warp writes four full 128-byte lines.
-    const int q = lane >> 3, c4 = (lane & 7) * 4;
-    // rp[tile row] = base address of that voice's output row (0 = none): 32 64-bit words per warp.  The four
-    // q-groups of a store read four neighbouring words (broadcast inside a group): conflict-free LDS.64.
+    // Output rows are indexed by the caller's voice index, which the bank has permuted (P_ROW).  Transposed
+    // write-back of a 64-frame tile: lanes 16q .. 16q+15 cover 256 contiguous bytes of tile row 2*i + q, so each
+    // STG.128 of the warp writes two runs of 256 bytes.
+    const int q = lane >> 4, c4 = (lane & 15) * 4;
+    // rp[tile row] = base address of that voice's output row (0 = none): 32 64-bit words per warp.  The two
+    // q-groups of a store read two neighbouring words (broadcast inside a group): conflict-free LDS.64.
     unsigned long long* rp = reinterpret_cast<unsigned long long*>(cold_base + kRows * kColdWords);
     float* ctab = cold_base + kRows * kColdWords + kRows * kRowPtrWords;
     bool all_rows;
@@ -195,310 +188,324 @@ render_kernel(const RenderArgs a) {
     uint32_t fast_left = 0, seg_left = 0, semi_left = 0;
     bool all_gconst = false, any_resting = false;
 
-    // Runs of tiles.  A third of the warp's stall time sits at the chunk boundaries (loop control, dispatch,
+    // Runs of tiles.  A third of the warp's stall time sits at the tile boundaries (loop control, dispatch,
     // store-variant selection: uniform-datapath code with exposed latencies, and the warps of an SM reach it in
     // lockstep), so when the store has its simple launch-uniform form — every tile row has an output row or no
     // rows are wanted, and the mix, if any, is the per-warp partial of a wide bank — the fast path renders up to
-    // kRunTiles tiles per trip round the outer loop, each followed by its own straight-line write-back (run lengths
-    // 2 / 4 / 8 / 16 measured 222 / 221 / 217 / 217 us per 65,536 x 4,096 block).
+    // kRunTiles tiles per trip round the outer loop, each followed by its own straight-line write-back.
 #ifndef S2_RUN_TILES
-#define S2_RUN_TILES 8
+#define S2_RUN_TILES 4
 #endif
     constexpr uint32_t kRunTiles = S2_RUN_TILES;
+    constexpr uint32_t kTile = kTileFrames;
+    // this warp's partial row of the mix, from launch parameters and the block index only (uniform registers: a
+    // pointer kept live across the chunk loop is spilled under the register cap and reloaded from local memory)
+    auto bus_row = [&]() -> float* {
+        return a.bus_partials + (size_t)(a.slot_begin / (uint32_t)kRows + blockIdx.x * (uint32_t)kWarpsPerBlock + (uint32_t)warp) * a.frames;
+    };
+    // (16-byte stores into the partial row: needs frames % 4 == 0 and an aligned base)
     const bool bus_wide_ok = a.bus_partials != nullptr && a.n_voices > 32u && (frames & 3u) == 0u &&
                              (reinterpret_cast<uintptr_t>(a.bus_partials) & 15u) == 0u;
     const bool simple_store = (gout == nullptr || all_rows) && (a.bus_partials == nullptr || bus_wide_ok) &&
                               (gout != nullptr || a.bus_partials != nullptr);
-    auto store_simple = [&](uint32_t ts) {
+    // Write-back of a full tile at frame ts.  ROWS: every tile row has an output row; MIX: per-warp partial sums of
+    // a wide bank — each lane adds its 16 rows as two pairwise trees of packed adds, then the two q-groups are added
+    // by one butterfly shuffle (a fixed tree: deterministic).  `checked`: rows may be missing (rp == 0).
+    auto store_tile = [&](uint32_t ts, bool rows, bool mix, bool checked) {
         const size_t tb = ((size_t)ts + (size_t)c4) * sizeof(float);
-        if (a.bus_partials == nullptr) {
+        if (!mix) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
-                const float4 val = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
-                __stcs(reinterpret_cast<float4*>(dst + tb), val);
+            for (int i = 0; i < 16; i++) {
+                char* dst = reinterpret_cast<char*>(rp[2 * i + q]);
+                const float4 val = *reinterpret_cast<const float4*>(tile + (2 * i + q) * kTileStride + c4);
+                if (!checked || dst) __stcs(reinterpret_cast<float4*>(dst + tb), val);
             }
         } else {
-            float4 val[8];
+            float2 s01 = make_float2(0.0f, 0.0f), s23 = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
-                if (gout) __stcs(reinterpret_cast<float4*>(reinterpret_cast<char*>(rp[4 * i + q]) + tb), val[i]);
-            }
-            float2 s01, s23;
-            tree_sum_rows<8>(val, s01, s23);
+            for (int hh = 0; hh < 2; hh++) {
+                float4 val[8];
 #pragma unroll
-            for (int sh = 8; sh <= 16; sh <<= 1) {
-                s01 = padd2(s01, make_float2(__shfl_xor_sync(0xffffffffu, s01.x, sh), __shfl_xor_sync(0xffffffffu, s01.y, sh)));
-                s23 = padd2(s23, make_float2(__shfl_xor_sync(0xffffffffu, s23.x, sh), __shfl_xor_sync(0xffffffffu, s23.y, sh)));
+                for (int i = 0; i < 8; i++) {
+                    const int r = 2 * (8 * hh + i) + q;
+                    val[i] = *reinterpret_cast<const float4*>(tile + r * kTileStride + c4);
+                    if (rows) {
+                        char* dst = reinterpret_cast<char*>(rp[r]);
+                        if (!checked || dst) __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
+                    }
+                }
+                float2 t01, t23;
+                tree_sum_rows<8>(val, t01, t23);
+                s01 = hh ? padd2(s01, t01) : t01;
+                s23 = hh ? padd2(s23, t23) : t23;
             }
-            float* gb = a.bus_partials + (size_t)(a.slot_begin / (uint32_t)kRows + blockIdx.x * (uint32_t)kWarpsPerBlock + (uint32_t)warp) * a.frames;
-            if (lane < 8) *reinterpret_cast<float4*>(gb + ts + c4) = make_float4(s01.x, s01.y, s23.x, s23.y);
+            s01 = padd2(s01, make_float2(__shfl_xor_sync(0xffffffffu, s01.x, 16), __shfl_xor_sync(0xffffffffu, s01.y, 16)));
+            s23 = padd2(s23, make_float2(__shfl_xor_sync(0xffffffffu, s23.x, 16), __shfl_xor_sync(0xffffffffu, s23.y, 16)));
+            if (lane < 16) *reinterpret_cast<float4*>(bus_row() + ts + c4) = make_float4(s01.x, s01.y, s23.x, s23.y);
         }
     };
-    auto clear_row = [&]() {
+    auto clear_chunk = [&](float* r) {
 #pragma unroll
         for (int j = 0; j < kChunk / 4; j++)
-            *reinterpret_cast<float4*>(row + 4 * j) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(r + 4 * j) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     };
 
-    for (uint32_t t0 = 0; t0 < frames; t0 += kChunk) {
-        const uint32_t cnt = min((uint32_t)kChunk, frames - t0);
-        const bool full = cnt == kChunk && t0 + kChunk <= f16 && a.force_path != 2u;
-        bool warp_fast = full && fast_left >= (uint32_t)kChunk;
-        bool warp_semi = full && !warp_fast && semi_left >= (uint32_t)kChunk;
-        if (full && !warp_fast && !warp_semi) {
-            // (Re)classify: which envelope segments is frame n in, and until when.
-            bool lane_fast = !active, lane_semi = !active;
-            uint32_t lane_left = 0xffffffffu;          // frames this lane's classification holds for
-            if (active) {
-                lane_fast = n + kChunk <= C.n_safe;
-                if (!lane_fast) {
-                    const float x0 = __uint2float_rn(n);
-                    const bool mm = (C.flags & 2u) != 0u;
-                    SegEnv sm = {0.0f, 0.0f, 0.0f, 0u, 1u << 24, 4};
-                    if (mm && n < (1u << 24)) sm = seg_env(C.L.mod, n);
-                    const bool mconst = !mm || !stage_moves(sm.stage);
-                    uint32_t n_safe = 0u;
-                    if (mconst && n < (1u << 24)) {
-                        // resting: the mod envelope is constant (sustain / end) or nothing follows it
-                        n_safe = mm ? sm.nend : 1u << 24;
-                        const float m = (mm && sm.stage == 2) ? C.L.mod.S : 0.0f;
-                        const float fo = modulate_freq(C.L.pitch, m, C.L.amt_osc);
-                        const float fl = modulate_freq(C.L.lpf, m, C.L.amt_lpf);
-                        OscC oc = C.oc;
-                        FiltC fc = C.fc;
-                        if (__float_as_uint(fo) != oc.fo_bits) { make_osc(oc, fo, sr); C.oc = oc; }
-                        if (__float_as_uint(fl) != fc.fl_bits) { make_filt<FILTER>(fc, fl, C.L.damp, sr); C.fc = fc; }
-                        // the fast phase step needs 1/P < 1 (and a sane period)
-                        const bool sane = oc.d < 1.0f && oc.P > 1.0f;
-                        if (!sane) n_safe = 0u;
-                        lane_fast = sane && n + kChunk <= n_safe;
-                        // publish into the lane's registers
-                        F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
-                        F.c0 = fc.c0; F.c1 = fc.c1; F.c2 = fc.c2;
-                    } else if (!mconst && C.L.amt_osc == 0.0f && n + kChunk <= sm.nend) {
-                        // the mod envelope ramps through the whole chunk and only the cutoff follows it: the period
-                        // is the per-voice constant sr / pitch -> moving-cutoff chunk
-                        OscC oc = C.oc;
-                        if (__float_as_uint(C.L.pitch) != oc.fo_bits) { make_osc(oc, C.L.pitch, sr); C.oc = oc; }
-                        if (oc.d < 1.0f && oc.P > 1.0f) {
-                            lane_semi = true;
-                            C.msg = sm;
+    for (uint32_t t0 = 0; t0 < frames; t0 += kTile) {
+        const uint32_t tcnt = min(kTile, frames - t0);
+        bool written = false;              // a run of fast tiles writes its tiles back itself
+        for (uint32_t h0 = 0; h0 < tcnt; h0 += kChunk) {
+            const uint32_t tc = t0 + h0;               // first frame of this chunk
+            float* crow = row + h0;
+            const uint32_t cnt = min((uint32_t)kChunk, frames - tc);
+            const bool full = cnt == kChunk && tc + kChunk <= f16 && a.force_path != 2u;
+            bool warp_fast = full && fast_left >= (uint32_t)kChunk;
+            bool warp_semi = full && !warp_fast && semi_left >= (uint32_t)kChunk;
+            if (full && !warp_fast && !warp_semi) {
+                // (Re)classify: which envelope segments is frame n in, and until when.
+                bool lane_fast = !active, lane_semi = !active;
+                uint32_t lane_left = 0xffffffffu;          // frames this lane's classification holds for
+                if (active) {
+                    lane_fast = n + kChunk <= C.n_safe;
+                    if (!lane_fast) {
+                        const bool mm = (C.flags & 2u) != 0u;
+                        SegEnv sm = {0.0f, 0.0f, 0.0f, 0u, 1u << 24, 4};
+                        if (mm && n < (1u << 24)) sm = seg_env(C.mod, n);
+                        const bool mconst = !mm || !stage_moves(sm.stage);
+                        uint32_t n_safe = 0u;
+                        if (mconst && n < (1u << 24)) {
+                            // resting: the mod envelope is constant (sustain / end) or nothing follows it
+                            n_safe = mm ? sm.nend : 1u << 24;
+                            const float m = (mm && sm.stage == 2) ? C.mod.S : 0.0f;
+                            const float fo = modulate_freq(C.pitch, m, C.amt_osc);
+                            const float fl = modulate_freq(C.lpf, m, C.amt_lpf);
+                            OscC oc = C.oc;
+                            FiltC fc = C.fc;
+                            if (__float_as_uint(fo) != oc.fo_bits) { make_osc(oc, fo, sr); C.oc = oc; }
+                            if (__float_as_uint(fl) != fc.fl_bits) { make_filt<FILTER>(fc, fl, C.damp, sr); C.fc = fc; }
+                            // the fast phase step needs 1/P < 1 (and a sane period)
+                            const bool sane = oc.d < 1.0f && oc.P > 1.0f;
+                            if (!sane) n_safe = 0u;
+                            lane_fast = sane && n + kChunk <= n_safe;
+                            // publish into the lane's registers
                             F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
+                            F.c0 = fc.c0; F.c1 = fc.c1; F.c2 = fc.c2;
+                        } else if (!mconst && C.amt_osc == 0.0f && n + kChunk <= sm.nend) {
+                            // the mod envelope ramps through the whole chunk and only the cutoff follows it: the period
+                            // is the per-voice constant sr / pitch -> moving-cutoff chunk
+                            OscC oc = C.oc;
+                            if (__float_as_uint(C.pitch) != oc.fo_bits) { make_osc(oc, C.pitch, sr); C.oc = oc; }
+                            if (oc.d < 1.0f && oc.P > 1.0f) {
+                                lane_semi = true;
+                                C.msg = sm;
+                                F.P = oc.P; F.d = oc.d; F.slope = oc.slope; F.nhalf = -oc.half; F.ts1 = oc.ts1; F.ts2 = oc.ts2;
+                            }
+                        }
+                        C.n_safe = n_safe;
+                    }
+                    if (lane_fast) { lane_left = C.n_safe - n; C.flags &= ~4u; }
+                    else if (lane_semi) { lane_left = C.msg.nend - n; C.flags |= 4u; }
+                    lane_semi |= lane_fast;
+                }
+                warp_fast = amask != 0u && __all_sync(0xffffffffu, lane_fast);
+                warp_semi = !warp_fast && amask != 0u && __all_sync(0xffffffffu, lane_semi);
+                fast_left = semi_left = 0;
+                if (warp_fast) fast_left = __reduce_min_sync(0xffffffffu, lane_left);
+                if (warp_semi) {
+                    semi_left = __reduce_min_sync(0xffffffffu, lane_left);
+                    any_resting = __any_sync(0xffffffffu, active && lane_fast);
+                }
+            }
+
+            if (warp_fast) {
+                if (seg_left < (uint32_t)kChunk) {
+                    // some lane's amp-envelope segment ends inside this chunk, or is not known yet: look again
+                    if (active && n >= F.seg_end) {
+                        const SegEnv sg = seg_env(C.amp, n);
+                        F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
+                        lane_gconst = sg.stage == 2 || sg.stage == 4;
+                    }
+                    seg_left = __reduce_min_sync(0xffffffffu, active ? F.seg_end - n : 0xffffffffu);
+                    all_gconst = __all_sync(0xffffffffu, lane_gconst);
+                }
+                const int gmode = seg_left >= (uint32_t)kChunk ? (all_gconst ? G_CONST : G_LINE) : G_ANY;
+                // Run: whole tiles for as long as the classification holds, each with its straight-line write-back
+                // (inactive voices run the same code on zeroed constants; their rows are cleared)
+                uint32_t reps = 0;
+                if (simple_store && gmode != G_ANY && h0 == 0u && tcnt == kTile)
+                    reps = min(min(min(fast_left, seg_left), f16 - t0) / kTile, kRunTiles);
+                const uint32_t n_chunks = reps ? reps * (kTile / (uint32_t)kChunk) : 1u;
+                uint32_t hh = h0, ts = t0;
+                for (uint32_t k = 0; k < n_chunks; k++) {
+                    switch (wkind) {
+                    case 0: fast_tile<FILTER, 0, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 1: fast_tile<FILTER, 1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 2: fast_tile<FILTER, 2, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 3: fast_tile<FILTER, 3, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    default: fast_tile<FILTER, -1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    }
+                    n += kChunk;
+                    hh += (uint32_t)kChunk;
+                    if (reps && hh == kTile) {
+                        if (!active) { clear_chunk(row); clear_chunk(row + kChunk); }
+                        __syncwarp();
+                        store_tile(ts, gout != nullptr, a.bus_partials != nullptr, false);
+                        __syncwarp();      // every lane is done reading the tile before the next one overwrites it
+                        hh = 0u;
+                        ts += kTile;
+                    }
+                }
+                fast_left -= n_chunks * (uint32_t)kChunk;
+                seg_left = gmode == G_ANY ? 0u : seg_left - n_chunks * (uint32_t)kChunk;
+                if (reps) {
+                    t0 += (reps - 1u) * kTile;               // the loop header adds the last tile
+                    written = true;
+                    break;
+                }
+            } else if (warp_semi) {
+                // Moving-cutoff chunk.  Lanes whose cutoff rests (flag 4 clear) run the same code on their constants.
+                MovV mv;
+                mv.moving = active && (C.flags & 4u) != 0u;
+                mv.cp.theta0 = C.theta0; mv.cp.amt = C.amt_lpf; mv.cp.damp = C.damp; mv.cp.hd = __fmul_rn(C.damp, 0.5f);
+                SegEnv sm = C.msg;
+                mv.mes = sm.es; mv.mnex0 = sm.nex0; mv.mey0 = sm.ey0;
+                mv.q_rest = C.fc.c1; mv.co_rest = C.fc.co;
+                constexpr bool kPackable = FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP;
+                if (filt_uniform) {
+                    // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once
+                    const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + leader * kColdWords);
+                    const uint32_t n_lead = __shfl_sync(0xffffffffu, n, leader);   // inactive lanes hold other offsets
+                    CutP cpl;
+                    cpl.theta0 = CL.theta0; cpl.amt = CL.amt_lpf; cpl.damp = CL.damp; cpl.hd = __fmul_rn(CL.damp, 0.5f);
+                    const SegEnv sml = CL.msg;
+                    modcut_coefficients<FILTER>(sml, cpl, one, n_lead, lane, ctab);
+                    __syncwarp();
+                    switch (wkind) {
+                    case 0: chunk_modcut_sc<FILTER, 0, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
+                    case 1: chunk_modcut_sc<FILTER, 1, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
+                    case 2: chunk_modcut_sc<FILTER, 2, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
+                    default: chunk_modcut_sc<FILTER, -1, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
+                    }
+                    __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
+                } else {
+                    // 0 = one frame at a time; 1 / 2 = packed at the window level every moving lane has
+                    int packed = 0;
+                    s2c::Window W;
+                    window_none(W);
+                    if constexpr (kPackable) {
+                        // the packed forms take the amp envelope as one line through the chunk (as G_LINE)
+                        if (active && n >= F.seg_end) {
+                            const SegEnv sg = seg_env(C.amp, n);
+                            F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
+                            lane_gconst = sg.stage == 2 || sg.stage == 4;
+                        }
+                        const bool one_seg = !active || n + kChunk <= F.seg_end;
+                        bool ok1 = one_seg, ok2 = one_seg;    // every lane: one amp segment; moving ones: aligned, level 1 / 2
+                        if (mv.moving && one_seg) {
+                            ok1 = ok2 = (n & 31u) == 0u;
+                            if (FILTER != FILT_ONE_POLE && ok1) {
+                                make_window_inl<FILTER>(W, sm, mv.cp, n);
+                                ok1 = W.valid == 1u;
+                                ok2 = W.valid == 2u;
+                            } else if (FILTER == FILT_ONE_POLE) {
+                                ok2 = false;
+                            }
+                        }
+                        if (a.force_path == 0u) {
+                            if (__all_sync(0xffffffffu, ok2) && FILTER != FILT_ONE_POLE) packed = 2;
+                            else if (__all_sync(0xffffffffu, ok1)) packed = 1;
                         }
                     }
-                    C.n_safe = n_safe;
-                }
-                if (lane_fast) { lane_left = C.n_safe - n; C.flags &= ~4u; }
-                else if (lane_semi) { lane_left = C.msg.nend - n; C.flags |= 4u; }
-                lane_semi |= lane_fast;
-            }
-            warp_fast = amask != 0u && __all_sync(0xffffffffu, lane_fast);
-            warp_semi = !warp_fast && amask != 0u && a.force_path != 2u && __all_sync(0xffffffffu, lane_semi);
-            fast_left = semi_left = 0;
-            if (warp_fast) fast_left = __reduce_min_sync(0xffffffffu, lane_left);
-            if (warp_semi) {
-                semi_left = __reduce_min_sync(0xffffffffu, lane_left);
-                any_resting = __any_sync(0xffffffffu, active && lane_fast);
-            }
-        }
-
-        if (warp_fast) {
-            if (seg_left < (uint32_t)kChunk) {
-                // some lane's amp-envelope segment ends inside this chunk, or is not known yet: look again
-                if (active && n >= F.seg_end) {
-                    const SegEnv sg = seg_env(C.L.amp, n);
-                    F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
-                    lane_gconst = sg.stage == 2 || sg.stage == 4;
-                }
-                seg_left = __reduce_min_sync(0xffffffffu, active ? F.seg_end - n : 0xffffffffu);
-                all_gconst = __all_sync(0xffffffffu, lane_gconst);
-            }
-            const int gmode = seg_left >= (uint32_t)kChunk ? (all_gconst ? G_CONST : G_LINE) : G_ANY;
-            // inactive voices run the same code on zeroed constants; their rows are cleared below
-            uint32_t reps = 1;
-            if (simple_store && gmode != G_ANY)
-                reps = min(min(min(fast_left, seg_left), f16 - t0) / (uint32_t)kChunk, kRunTiles);      // >= 1
-            for (uint32_t r = 0;;) {
-                switch (wkind) {
-                case 0: fast_tile<FILTER, 0, TRACE>(gmode, fasthash, F, &C.L.amp, one, kind, rot, n, row, sintab); break;
-                case 1: fast_tile<FILTER, 1, TRACE>(gmode, fasthash, F, &C.L.amp, one, kind, rot, n, row, sintab); break;
-                case 2: fast_tile<FILTER, 2, TRACE>(gmode, fasthash, F, &C.L.amp, one, kind, rot, n, row, sintab); break;
-                case 3: fast_tile<FILTER, 3, TRACE>(gmode, fasthash, F, &C.L.amp, one, kind, rot, n, row, sintab); break;
-                default: fast_tile<FILTER, -1, TRACE>(gmode, fasthash, F, &C.L.amp, one, kind, rot, n, row, sintab); break;
+                    if (packed) {
+                        if constexpr (kPackable) {
+                            constexpr bool kCanInterp = FILTER != FILT_ONE_POLE;
+                            auto run = [&](auto kind_tag) {
+                                constexpr int K = decltype(kind_tag)::value;
+                                if (packed == 1) {
+                                    if (any_resting) chunk_modcut_pk<FILTER, K, true, false, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
+                                    else chunk_modcut_pk<FILTER, K, false, false, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
+                                } else if constexpr (kCanInterp) {
+                                    if (fasthash) chunk_modcut_pk<FILTER, K, false, true, true, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
+                                    else chunk_modcut_pk<FILTER, K, false, true, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
+                                }
+                            };
+                            switch (wkind) {
+                            case 0: run(std::integral_constant<int, 0>{}); break;
+                            case 1: run(std::integral_constant<int, 1>{}); break;
+                            default: run(std::integral_constant<int, -1>{}); break;
+                            }
+                        }
+                    } else {
+                        chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, nullptr);
+                    }
                 }
                 n += kChunk;
-                if (!simple_store) break;                    // one tile, written back by the common code below
-                if (!active) clear_row();
-                __syncwarp();
-                store_simple(t0 + r * (uint32_t)kChunk);
-                __syncwarp();      // every lane is done reading the tile before the next one overwrites it
-                if (++r == reps) break;
-            }
-            fast_left -= reps * (uint32_t)kChunk;
-            seg_left = gmode == G_ANY ? 0u : seg_left - reps * (uint32_t)kChunk;
-            if (simple_store) {
-                t0 += (reps - 1u) * (uint32_t)kChunk;        // the loop header adds the last tile
-                continue;
-            }
-        } else if (warp_semi) {
-            // Moving-cutoff chunk.  Lanes whose cutoff rests (flag 4 clear) run the same code on their constants.
-            MovV mv;
-            mv.moving = active && (C.flags & 4u) != 0u;
-            mv.cp.theta0 = C.theta0; mv.cp.amt = C.L.amt_lpf; mv.cp.damp = C.L.damp; mv.cp.hd = __fmul_rn(C.L.damp, 0.5f);
-            SegEnv sm = C.msg;
-            mv.mes = sm.es; mv.mnex0 = sm.nex0; mv.mey0 = sm.ey0;
-            constexpr bool kPackable = FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP;
-            if (filt_uniform) {
-                // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once
-                const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + leader * kColdWords);
-                const uint32_t n_lead = __shfl_sync(0xffffffffu, n, leader);   // inactive lanes hold other offsets
-                CutP cpl;
-                cpl.theta0 = CL.theta0; cpl.amt = CL.L.amt_lpf; cpl.damp = CL.L.damp; cpl.hd = __fmul_rn(CL.L.damp, 0.5f);
-                const SegEnv sml = CL.msg;
-                modcut_coefficients<FILTER>(sml, cpl, one, n_lead, lane, ctab);
-                __syncwarp();
-                switch (wkind) {
-                case 0: chunk_modcut_sc<FILTER, 0, TRACE, true>(F, &C.L.amp, mv, sm, one, kind, rot, n, row, sintab, ctab); break;
-                case 1: chunk_modcut_sc<FILTER, 1, TRACE, true>(F, &C.L.amp, mv, sm, one, kind, rot, n, row, sintab, ctab); break;
-                case 2: chunk_modcut_sc<FILTER, 2, TRACE, true>(F, &C.L.amp, mv, sm, one, kind, rot, n, row, sintab, ctab); break;
-                default: chunk_modcut_sc<FILTER, -1, TRACE, true>(F, &C.L.amp, mv, sm, one, kind, rot, n, row, sintab, ctab); break;
-                }
-                __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
+                semi_left -= (uint32_t)kChunk;
+                seg_left = 0u;             // the amp segment registers were not kept up to date
             } else {
-                bool packed = false;
-                s2c::Window W;
-                W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
-                if constexpr (kPackable) {
-                    bool lane_ok = true;
-                    if (mv.moving) {
-                        lane_ok = (n & 31u) == 0u;
-                        if (FILTER != FILT_ONE_POLE && lane_ok) {
-                            make_window<FILTER>(W, sm, mv.cp, n);
-                            lane_ok = W.valid != 0u;
-                        }
+                if (active) {
+                    // the general path derives everything again from the voice's parameter column
+                    const Lane L = load_lane(a.params + C.vi, vp, sr);
+                    OscC oc = C.oc;
+                    FiltC fc = C.fc;
+                    MovG mg;
+                    movg_init(mg, L.lpf, L.amt_lpf, L.damp, sr);
+                    float ph = F.ph;
+                    FiltS fs = {F.x1, F.x2, F.y1, F.y2};
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const bool scalar_sem = tc + i >= f16;
+                        crow[i] = general_frame<FILTER, TRACE>(L, sr, one, n, scalar_sem, oc, fc, mg, ph, fs, sintab);
+                        n += 1u;
                     }
-                    packed = a.force_path == 0u && __all_sync(0xffffffffu, lane_ok);
+                    C.oc = oc;
+                    C.fc = fc;
+                    F.ph = ph;
+                    F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+                    C.n_safe = 0u;         // oc/fc may have moved: republish through the classifier
                 }
-                if (packed) {
-                    if constexpr (kPackable) {
-                        if (any_resting) {
-                            switch (wkind) {
-                            case 0: chunk_modcut_pk<FILTER, 0, true, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            case 1: chunk_modcut_pk<FILTER, 1, true, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            default: chunk_modcut_pk<FILTER, -1, true, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            }
-                        } else {
-                            switch (wkind) {
-                            case 0: chunk_modcut_pk<FILTER, 0, false, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            case 1: chunk_modcut_pk<FILTER, 1, false, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            default: chunk_modcut_pk<FILTER, -1, false, TRACE>(F, &C.L.amp, mv, W, one, kind, rot, n, row, sintab); break;
-                            }
-                        }
-                    }
-                } else {
-                    chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.L.amp, mv, sm, one, kind, rot, n, row, sintab, nullptr);
-                }
+                fast_left = semi_left = seg_left = 0u;
             }
-            n += kChunk;
-            semi_left -= (uint32_t)kChunk;
-            seg_left = 0u;             // the amp segment registers were not kept up to date
-            if (simple_store) {
-                if (!active) clear_row();
-                __syncwarp();
-                store_simple(t0);
-                __syncwarp();
-                continue;
-            }
-        } else {
-            if (active) {
-                const Lane L = C.L;
-                OscC oc = C.oc;
-                FiltC fc = C.fc;
-                MovG mg;
-                movg_init(mg, L.lpf, L.amt_lpf, L.damp, sr);
-                float ph = F.ph;
-                FiltS fs = {F.x1, F.x2, F.y1, F.y2};
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const bool scalar_sem = t0 + i >= f16;
-                    row[i] = general_frame<FILTER, TRACE>(L, sr, one, n, scalar_sem, oc, fc, mg, ph, fs, sintab);
-                    n += 1u;
-                }
-                C.oc = oc;
-                C.fc = fc;
-                F.ph = ph;
-                F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
-                C.n_safe = 0u;         // oc/fc may have moved: republish through the classifier
-            }
-            fast_left = semi_left = seg_left = 0u;
+            if (!active) clear_chunk(crow);
         }
-        if (!active) clear_row();
+        if (written) continue;
+        // ---- write-back of this tile (tcnt frames)
         __syncwarp();
-        // (16-byte stores into this warp's partial row: needs frames % 4 == 0 and an aligned base)
-        // this warp's partial row, from launch parameters and the block index only (uniform registers: a pointer
-        // kept live across the chunk loop is spilled under the register cap and reloaded from local memory)
-        float* __restrict__ gbus = a.bus_partials
-            ? a.bus_partials + (size_t)(a.slot_begin / (uint32_t)kRows + blockIdx.x * (uint32_t)kWarpsPerBlock + (uint32_t)warp) * a.frames
-            : nullptr;
-        const bool wide_bus = gbus != nullptr && a.n_voices > 32u && cnt == kChunk && (frames & 3u) == 0u &&
-                              (reinterpret_cast<uintptr_t>(gbus) & 15u) == 0u;
-        float2 b01 = make_float2(0.0f, 0.0f), b23 = make_float2(0.0f, 0.0f);
-        if (cnt == kChunk && (gout || wide_bus)) {
-            // One pass over the tile, transposed: lane (q, c4) reads 16 bytes of rows 4*i + q.  For banks
-            // wider than a warp the same registers also feed the bus: each lane adds its 8 rows, then the
-            // four q-groups are added by two butterfly shuffles (a fixed tree: deterministic; banks of <= 32
-            // voices use the reference's sequential order below).
-            const size_t tb = ((size_t)t0 + (size_t)c4) * sizeof(float);
-            float4 val[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                val[i] = *reinterpret_cast<const float4*>(tile + (4 * i + q) * kTileStride + c4);
-                if (gout) {
-                    char* dst = reinterpret_cast<char*>(rp[4 * i + q]);
-                    if (dst) __stcs(reinterpret_cast<float4*>(dst + tb), val[i]);
-                }
-            }
-            if (wide_bus) tree_sum_rows<8>(val, b01, b23);
+        float* __restrict__ gbus = a.bus_partials ? bus_row() : nullptr;
+        const bool wide_bus = gbus != nullptr && bus_wide_ok && tcnt == kTile;
+        if (tcnt == kTile && (gout || wide_bus)) {
+            store_tile(t0, gout != nullptr, wide_bus, !all_rows);
         } else if (gout) {
             for (uint32_t r = 0; r < 32u; r++) {
                 const uint32_t orow = __shfl_sync(0xffffffffu, C.out_row, r);
-                if (orow != 0xffffffffu && (uint32_t)lane < cnt)
-                    gout[(size_t)orow * stride + t0 + lane] = tile[r * kTileStride + lane];
+                if (orow != 0xffffffffu)
+                    for (uint32_t c = (uint32_t)lane; c < tcnt; c += 32u)
+                        gout[(size_t)orow * stride + t0 + c] = tile[r * kTileStride + c];
             }
         }
-        if (wide_bus) {
-#pragma unroll
-            for (int sh = 8; sh <= 16; sh <<= 1) {
-                b01 = padd2(b01, make_float2(__shfl_xor_sync(0xffffffffu, b01.x, sh), __shfl_xor_sync(0xffffffffu, b01.y, sh)));
-                b23 = padd2(b23, make_float2(__shfl_xor_sync(0xffffffffu, b23.x, sh), __shfl_xor_sync(0xffffffffu, b23.y, sh)));
-            }
-            if (lane < 8) *reinterpret_cast<float4*>(gbus + t0 + c4) = make_float4(b01.x, b01.y, b23.x, b23.y);
-        } else if (gbus) {
-            if ((uint32_t)lane < cnt) {
+        if (gbus && !wide_bus) {
+            for (uint32_t c = (uint32_t)lane; c < tcnt; c += 32u) {
                 float acc;
                 if (a.n_voices <= 32u) {
                     // synth.rs:176-202: voices are accumulated in index order, starting from 0.0 — the
                     // reference's exact summation order (a bank this narrow is one warp, identity slots)
                     acc = 0.0f;
 #pragma unroll 8
-                    for (int r = 0; r < kRows; r++) acc = __fadd_rn(acc, tile[r * kTileStride + lane]);
+                    for (int r = 0; r < kRows; r++) acc = __fadd_rn(acc, tile[r * kTileStride + c]);
                 } else {
-                    // ragged last chunk of a wide bank: fixed 4-way tree over the warp's rows
+                    // ragged last tile of a wide bank: fixed 4-way tree over the warp's rows
                     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
                     for (int r = 0; r < kRows; r += 4) {
-                        a0 = __fadd_rn(a0, tile[(r + 0) * kTileStride + lane]);
-                        a1 = __fadd_rn(a1, tile[(r + 1) * kTileStride + lane]);
-                        a2 = __fadd_rn(a2, tile[(r + 2) * kTileStride + lane]);
-                        a3 = __fadd_rn(a3, tile[(r + 3) * kTileStride + lane]);
+                        a0 = __fadd_rn(a0, tile[(r + 0) * kTileStride + c]);
+                        a1 = __fadd_rn(a1, tile[(r + 1) * kTileStride + c]);
+                        a2 = __fadd_rn(a2, tile[(r + 2) * kTileStride + c]);
+                        a3 = __fadd_rn(a3, tile[(r + 3) * kTileStride + c]);
                     }
                     acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
                 }
-                gbus[t0 + lane] = acc;
+                gbus[t0 + c] = acc;
             }
         }
-        __syncwarp();      // every lane is done reading the tile before the next chunk overwrites it
+        __syncwarp();      // every lane is done reading the tile before the next one overwrites it
     }
 
     if (active) {
@@ -519,8 +526,8 @@ render_kernel(const RenderArgs a) {
         S[S_OSC_P * vp] = oc.P; S[S_OSC_D * vp] = oc.d; S[S_OSC_SLOPE * vp] = oc.slope;
         S[S_OSC_HALF * vp] = oc.half; S[S_OSC_TS1 * vp] = oc.ts1; S[S_OSC_TS2 * vp] = oc.ts2;
         S[S_FL_KEY * vp] = __uint_as_float(fc.fl_bits);
-        S[S_DAMP_KEY * vp] = C.L.damp;
-        S[S_FC_C0 * vp] = fc.c0; S[S_FC_C1 * vp] = fc.c1; S[S_FC_C2 * vp] = fc.c2;
+        S[S_DAMP_KEY * vp] = C.damp;
+        S[S_FC_C0 * vp] = fc.c0; S[S_FC_C1 * vp] = fc.c1; S[S_FC_C2 * vp] = fc.c2; S[S_FC_CO * vp] = fc.co;
     }
 }
 
