@@ -215,7 +215,7 @@ uint64_t s2_launch_count(void);
 int s2_synth_new(int device, s2_synth** out);                         /* Synth::new()  synth.rs:54-59 */
 void s2_synth_free(s2_synth* synth);
 int s2_synth_note_on(s2_synth* synth, uint8_t note, float velocity);  /* synth.rs:61-70 */
-int s2_synth_note_off(s2_synth* synth, uint8_t note);                 /* synth.rs:72-80; returns 1 on "released twice" */
+int s2_synth_note_off(s2_synth* synth, uint8_t note);                 /* synth.rs:72-80; a note no voice holds (or one already released) is ignored */
 /* Synth::sample(&mut self, buffer: &mut [f32], sample_rate) synth.rs:154-169: overwrites
    `frames` floats of HOST memory with the mono mix of the 8 voices. */
 int s2_synth_sample(s2_synth* synth, float* h_buffer, size_t frames, uint32_t sample_rate);

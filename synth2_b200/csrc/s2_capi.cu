@@ -58,7 +58,11 @@ int set_error(int code, const char* fmt, ...) {
 
 namespace {
 
-int validate_voice(const s2_voice_desc& d, size_t index) {
+int validate_voice(const s2_voice_desc& d, size_t index, uint32_t filter_kind = S2_FILTER_ONE_POLE) {
+    // second-order filters: damping (band-pass: the quality factor) divides or scales the coefficients
+    // (dsp_filters.rs:99-109, 197-207; 0.2 is the documented minimum, :94-96); zero gives tan(inf) / a zero denominator
+    if (filter_kind >= S2_FILTER_BIQUAD_LP && filter_kind <= S2_FILTER_BIQUAD_BP && !(d.damping > 0.0f))
+        return fail(S2_ERR_INVALID, "voice %zu: damping must be > 0 for the second-order filters", index);
     if (d.osc_kind > S2_OSC_SINE) return fail(S2_ERR_INVALID, "voice %zu: osc_kind %u", index, d.osc_kind);
     if (!(std::isfinite(d.pitch_hz) && d.pitch_hz > 0.0f))
         return fail(S2_ERR_INVALID, "voice %zu: pitch_hz must be finite and > 0", index);
@@ -387,8 +391,16 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
         if (((uintptr_t)d_voice_out & 15u) != 0 || (row_stride & 3u) != 0 || row_stride < frames)
             return fail(S2_ERR_INVALID, "voice_out must be 16-byte aligned with row_stride %% 4 == 0 and >= frames");
     }
-    if (b->max_offset + frames > 0xFFFFFFFFull)
-        return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
+    if (b->max_offset + frames > 0xFFFFFFFFull) {
+        // max_offset is an upper bound that only grows with the frames rendered; voices restarted since then sit at
+        // small offsets.  Look at the real ones before failing (the reference panics only when a voice's own offset
+        // overflows, process.rs:36): O(V), and only when the bound trips.
+        uint64_t mx = 0;
+        for (size_t i = 0; i < b->n_voices; i++)
+            if (b->book[i].active) mx = std::max<uint64_t>(mx, (uint64_t)b->book[i].start_offset + (b->total_frames - b->book[i].start_total));
+        b->max_offset = mx;
+        if (mx + frames > 0xFFFFFFFFull) return fail(S2_ERR_OVERFLOW, "frame offset overflow (process.rs:36)");
+    }
     CUDA_TRY(cudaSetDevice(b->device));
     if (trace == s2::TRACE_NONE) {
         const int cls = ts_block_class(b, frames, d_voice_out, d_bus_out);
@@ -502,7 +514,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
         return fail(S2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= ndev) return fail(S2_ERR_NO_DEVICE, "device %d out of range (%d)", device, ndev);
     for (size_t i = 0; i < n_voices; i++) {
-        int rc = validate_voice(voices[i], i);
+        int rc = validate_voice(voices[i], i, filter_kind);
         if (rc) return rc;
     }
     CUDA_TRY(cudaSetDevice(device));
@@ -629,7 +641,7 @@ size_t s2_bank_voices(const s2_bank* b) { return b ? b->n_voices : 0; }
 int s2_bank_set_voice(s2_bank* b, size_t index, const s2_voice_desc* voice) {
     if (!b || !voice) return fail(S2_ERR_INVALID, "null argument");
     if (index >= b->n_voices) return fail(S2_ERR_INVALID, "voice index %zu out of range", index);
-    int rc = validate_voice(*voice, index);
+    int rc = validate_voice(*voice, index, b->filter_kind);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(b->device));
     if ((rc = bank_drain(b)) != S2_OK) return rc;      // pipelined mode: per-voice edits are not pipelined
@@ -979,8 +991,8 @@ int s2_synth_note_off(s2_synth* s, uint8_t note) {
     SynthVoice& v = s->voices[found];
     v.has_release = true;
     v.release = synth_current(s, found);
+    s->pending[found].release_offset = v.release;      // the description mirrors the bank (rebuilds start from it)
     if (s->dirty[found] || !s->bank) {
-        s->pending[found].release_offset = v.release;
         s->dirty[found] = true;
         return S2_OK;
     }
@@ -999,6 +1011,8 @@ static int synth_ensure_bank(s2_synth* s, uint32_t sample_rate) {
         for (int i = 0; i < kNumVoices; i++) {
             ds[i] = s->pending[i];
             if (!s->dirty[i]) ds[i].frame_offset = st[i].frame_offset;
+            // a note_off on an uploaded voice went straight to the bank: the description must carry it too
+            ds[i].release_offset = s->voices[i].has_release ? s->voices[i].release : S2_NO_RELEASE;
         }
         s2_bank* nb = nullptr;
         rc = s2_bank_create(s->device, sample_rate, s->patch.filter_kind, kNumVoices, ds.data(), nullptr, &nb);
@@ -1035,15 +1049,27 @@ int s2_synth_set_patch(s2_synth* s, const s2_patch* patch) {
     if (patch->filter_kind > S2_FILTER_FIRST_ORDER_HP) return fail(S2_ERR_INVALID, "filter_kind %u", patch->filter_kind);
     s2_voice_desc probe = patch->voice;
     probe.pitch_hz = 440.0f;                    // the template's pitch is replaced per note
-    int rc = validate_voice(probe, 0);
+    int rc = validate_voice(probe, 0, patch->filter_kind);
     if (rc) return rc;
     if (patch->filter_kind != s->patch.filter_kind) {
-        for (int i = 0; i < kNumVoices; i++)
-            if (s->voices[i].has_current)
-                return fail(S2_ERR_INVALID, "the filter kind can only change while no voice is sounding");
+        // a voice sounds from its note_on until its amp envelope has ended: release start = max(release, A + D)
+        // (old/simdtest.rs:283-285), end = start + R; `has_current` alone never clears (synth.rs:23-30)
+        for (int i = 0; i < kNumVoices; i++) {
+            const SynthVoice& v = s->voices[i];
+            if (!v.has_current) continue;
+            bool sounding = !v.has_release;
+            if (v.has_release) {
+                const s2_voice_desc& d = s->pending[i];
+                const double sr = s->sample_rate ? (double)s->sample_rate : 48000.0;
+                const double ad = sr * ((double)d.amp_attack_ms + (double)d.amp_decay_ms) / 1000.0;
+                const double end = std::max((double)v.release, ad) + sr * (double)d.amp_release_ms / 1000.0 + 1.0;
+                sounding = (double)synth_current(s, i) < end;
+            }
+            if (sounding) return fail(S2_ERR_INVALID, "the filter kind can only change while no voice is sounding");
+        }
         s2_bank_destroy(s->bank);               // the next render builds a bank of the new kind
         s->bank = nullptr;
-        for (int i = 0; i < kNumVoices; i++) { s2_default_voice(&s->pending[i]); s->dirty[i] = false; }
+        for (int i = 0; i < kNumVoices; i++) { s2_default_voice(&s->pending[i]); s->dirty[i] = false; s->voices[i] = SynthVoice(); }
     }
     s->patch = *patch;
     s->patch.name[sizeof s->patch.name - 1] = 0;

@@ -696,103 +696,89 @@ struct MovV {
 
 // Moving-cutoff chunk, packed: the period is constant but the mod envelope is in a ramp, so the cutoff — and with
 // it the filter coefficients — changes every frame (process.rs:148-152, 363-371; the first 200 ms of every note of
-// the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every moving lane): the
-// chunk starts at a multiple of 32 frames, lies inside one segment of the mod envelope, and (second-order
-// filters) its window W is valid — at level 2 for INTERP (q and cos at every 4th frame, linear in between), at
-// level 1 otherwise (every frame); the chunk also lies inside the lane's current amp-envelope segment (F.es ..,
-// as G_LINE).  Everything in packed arithmetic on frames (i, i + 1) (s2_cutoff.h).  MIXED: some lanes' cutoffs rest;
-// they select their constants.
-template <int FILTER, int KIND, bool MIXED, bool INTERP, bool FASTHASH, int TRACE>
+// the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every lane): the chunk lies
+// inside the lane's current amp-envelope segment (F.es .., as G_LINE); for every MOVING lane it starts at a multiple
+// of 32 frames, lies inside one segment of the mod envelope, and (second-order filters) its window W is valid at
+// level 2: q and cos at every 4th frame, linear in between, the coefficient algebra per frame (s2_cutoff.h).  The
+// one-pole evaluates k = e^-theta every frame.  Lanes whose cutoff rests run the same code: their interpolation
+// nodes are their own 2 beta and cos(theta), which the algebra turns into their resting coefficients bit for bit
+// (one-pole: they select their constants).
+// ONE variant per oscillator kind and 4 frames per trip, on purpose: a moving-cutoff step walks through the
+// classifier, the window's binary64 code, this loop and the write-back once per chunk, and with 8-frame trips in
+// four variants that path outgrew the 32 KB instruction cache of an SM — 41 % of the stall samples of such a launch
+// were instruction fetch (profiles/r2_notes.md).
+template <int FILTER, int KIND, int TRACE>
 __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const s2c::Window& W,
                                                 float one, uint32_t kind, uint32_t rot, uint32_t n0,
                                                 float* __restrict__ row, const float* sintab) {
     static_assert(FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
-    static_assert(!INTERP || FILTER != FILT_ONE_POLE, "the one-pole evaluates every frame");
+    constexpr bool INTERP = FILTER != FILT_ONE_POLE;
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
     uint32_t n = n0;
     float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     float ph = F.ph;
-    uint32_t nbc = 0;                 // FASTHASH: hash of the trip's first frame (see chunk_fast_tp)
     auto mod2 = [&](float2 x2) {      // the mod envelope's line at two frame offsets
         return s2c::vaddp(pmul2(splat2(mv.mes), padd2(x2, splat2(mv.mnex0))), splat2(mv.mey0), one);
     };
-    // one pair of frames with coefficients (c0, c1, c2) per frame; fi = index of the pair's first frame in its trip
-    auto pair = [&](float2 c0, float2 c1, float2 c2, uint32_t fi, float* o2) {
-        FiltC ca, cb;
-        if (MIXED && !mv.moving) {
-            ca.c0 = cb.c0 = F.c0; ca.c1 = cb.c1 = F.c1; ca.c2 = cb.c2 = F.c2;
-        } else {
+    // nodes of the interpolation: (q, cos) at frames (x, x + 4)
+    auto nodes = [&](float x, float2* q, float2* co) {
+        s2c::node_q_cos<float2>(W, mod2(make_float2(x, __fadd_rn(x, 4.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, q, co);
+        if (!mv.moving) { *q = splat2(mv.q_rest); *co = splat2(mv.co_rest); }
+    };
+    float2 qP = splat2(0.0f), coP = splat2(0.0f);
+    float q0 = 0.0f, co0 = 0.0f;
+    if (INTERP) {
+        nodes(xf2.x, &qP, &coP);       // frames n0 and n0 + 4
+        q0 = qP.x; co0 = coP.x;
+    }
+#pragma unroll 1
+    for (int j = 0; j < kChunk / 4; j++) {
+        float dq = 0.0f, dco = 0.0f;
+        if (INTERP) {
+            // frames [4j, 4j + 4): from node 4j (q0, co0) to node 4j + 4 — the second of the pair evaluated one trip
+            // ago on even trips, the first of the pair evaluated now (frames 4j + 4, 4j + 8) on odd ones
+            if (j & 1) nodes(__fadd_rn(xf2.x, 4.0f), &qP, &coP);
+            const float q1 = (j & 1) ? qP.x : qP.y, co1 = (j & 1) ? coP.x : coP.y;
+            dq = __fmul_rn(__fsub_rn(q1, q0), 0.25f);
+            dco = __fmul_rn(__fsub_rn(co1, co0), 0.25f);
+        }
+        float o4[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float2 c0, c1, c2;
+            if (INTERP) {
+                const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
+                s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(q0)), pfma2(j2, splat2(dco), splat2(co0)),
+                                                                         one, &c0, &c1, &c2);
+            } else {
+                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(mod2(xf2), mv.cp.amt, mv.cp.theta0));
+                c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
+                c2 = splat2(0.0f);
+                if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); }
+            }
+            FiltC ca, cb;
             ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
             cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
+            const float pa = ph;
+            const float pb = wrap_unit(__fadd_rn(pa, F.d));
+            ph = wrap_unit(__fadd_rn(pb, F.d));
+            const float2 ph2 = make_float2(pa, pb);
+            const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
+            const uint32_t ha = (rot ^ n) * 0x9e3779b9u, hb = (rot ^ (n + 1u)) * 0x9e3779b9u;
+            const float2 u2 = input2<false>(F, osc2, ha, hb);
+            const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
+            const float2 g2 = s2c::vaddp(pmul2(splat2(F.es), padd2(xf2, splat2(F.nex0))), splat2(F.ey0), one);
+            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
+            o4[2 * h] = out2.x;
+            o4[2 * h + 1] = out2.y;
+            n += 2u;
+            xf2 = padd2(xf2, splat2(2.0f));
         }
-        const float pa = ph;
-        const float pb = wrap_unit(__fadd_rn(pa, F.d));
-        ph = wrap_unit(__fadd_rn(pb, F.d));
-        const float2 ph2 = make_float2(pa, pb);
-        const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
-        const uint32_t ha = FASTHASH ? nbc + fi * 0x9e3779b9u : (rot ^ n) * 0x9e3779b9u;
-        const uint32_t hb = FASTHASH ? nbc + (fi + 1u) * 0x9e3779b9u : (rot ^ (n + 1u)) * 0x9e3779b9u;
-        const float2 u2 = input2<FASTHASH>(F, osc2, ha, hb);
-        const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
-        const float2 g2 = s2c::vaddp(pmul2(splat2(F.es), padd2(xf2, splat2(F.nex0))), splat2(F.ey0), one);
-        const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
-        o2[0] = out2.x;
-        o2[1] = out2.y;
-        n += 2u;
-        xf2 = padd2(xf2, splat2(2.0f));
-    };
-    if constexpr (INTERP) {
-        // nodes n0, n0 + 4 now; inside the loop the next two, one 8-frame trip ahead.  A resting lane's nodes are its
-        // own 2 beta and cos(theta): the same algebra then reproduces its resting coefficients bit for bit (make_filt).
-        float2 qA, coA;
-        s2c::node_q_cos<float2>(W, mod2(padd2(splat2(xf2.x), make_float2(0.0f, 4.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, &qA, &coA);
-        if (!mv.moving) { qA = splat2(mv.q_rest); coA = splat2(mv.co_rest); }
-#pragma unroll 1
-        for (int jt = 0; jt < kChunk / 8; jt++) {
-            if (FASTHASH) nbc = (rot ^ n) * 0x9e3779b9u;
-            float2 qB, coB;
-            s2c::node_q_cos<float2>(W, mod2(padd2(splat2(xf2.x), make_float2(8.0f, 12.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, &qB, &coB);
-            if (!mv.moving) { qB = qA; coB = coA; }
-#pragma unroll
-            for (int sgi = 0; sgi < 2; sgi++) {
-                const float qa = sgi ? qA.y : qA.x, qb = sgi ? qB.x : qA.y;
-                const float ca = sgi ? coA.y : coA.x, cb = sgi ? coB.x : coA.y;
-                const float dq = __fmul_rn(__fsub_rn(qb, qa), 0.25f), dco = __fmul_rn(__fsub_rn(cb, ca), 0.25f);
-                float o4[4];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
-                    float2 c0, c1, c2;
-                    s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(qa)), pfma2(j2, splat2(dco), splat2(ca)),
-                                                                             one, &c0, &c1, &c2);
-                    pair(c0, c1, c2, 4u * sgi + 2u * h, o4 + 2 * h);
-                }
-                *reinterpret_cast<float4*>(row + 8 * jt + 4 * sgi) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-            }
-            qA = qB; coA = coB;
-        }
-    } else {
-#pragma unroll 1
-        for (int j = 0; j < kChunk / 4; j++) {
-            if (FASTHASH && (j & 1) == 0) nbc = (rot ^ n) * 0x9e3779b9u;
-            float o4[4];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const float2 m2 = mod2(xf2);
-                float2 c0, c1, c2;
-                if (FILTER == FILT_ONE_POLE) {
-                    c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
-                    c1 = pfma2(c0, splat2(-one), splat2(1.0f));           // 1 - k, one rounding (exact product)
-                    c2 = splat2(0.0f);
-                } else {
-                    float2 s2v, co2;
-                    s2c::window_sincos<float2>(W, s2c::delta_at<float2>(m2, mv.cp.amt, mv.cp.theta0, W.thc), &s2v, &co2);
-                    s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2v, co2, mv.cp.hd, one, &c0, &c1, &c2);
-                }
-                pair(c0, c1, c2, 4u * (j & 1) + 2u * h, o4 + 2 * h);
-            }
-            *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        if (INTERP) {
+            q0 = (j & 1) ? qP.x : qP.y;
+            co0 = (j & 1) ? coP.x : coP.y;
         }
     }
     F.ph = ph;

@@ -14,12 +14,13 @@
 
 #include <type_traits>
 
-// Register cap of the render kernel, as a minimum of resident one-warp blocks per SM: 20 blocks = 65,536 / (20 * 32)
-// = 102 -> 96 registers.  96 keeps the fast loops spill-free and lets 16+ one-warp blocks share an SM, so blocks of
-// overlapping launches (pipelined mode) find room: measured 1.079e12 voice-samples/s at 96 against 1.047e12 at 128
-// and 0.967e12 at 80 (spills).
+// Register cap of the render kernel, as a minimum of resident one-warp blocks per SM: 16 blocks = 65,536 / (16 * 32)
+// = 128 registers.  Shared memory (14.8 KB + 1 KB per block) already limits an SM to 14 blocks — the 13.8 a
+// 65,536-voice bank needs — so nothing is lost against the 96 registers of round 1, and the chunk-level state
+// (classification counters, tile pointers) no longer spills around the inlined loops: the spill reloads sat at
+// the head of every chunk and showed as long-scoreboard stalls (21 % of the samples of a moving-cutoff launch).
 #ifndef S2_MINBLOCKS
-#define S2_MINBLOCKS 20
+#define S2_MINBLOCKS 16
 #endif
 
 namespace s2 {
@@ -387,51 +388,34 @@ render_kernel(const RenderArgs a) {
                     }
                     __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
                 } else {
-                    // 0 = one frame at a time; 1 / 2 = packed at the window level every moving lane has
-                    int packed = 0;
+                    // packed: every lane inside one amp segment; moving ones aligned and (second-order filters) with a
+                    // window at level 2.  Otherwise one frame at a time.
+                    bool packed = false;
                     s2c::Window W;
                     window_none(W);
                     if constexpr (kPackable) {
-                        // the packed forms take the amp envelope as one line through the chunk (as G_LINE)
+                        // the packed form takes the amp envelope as one line through the chunk (as G_LINE)
                         if (active && n >= F.seg_end) {
                             const SegEnv sg = seg_env(C.amp, n);
                             F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
                             lane_gconst = sg.stage == 2 || sg.stage == 4;
                         }
-                        const bool one_seg = !active || n + kChunk <= F.seg_end;
-                        bool ok1 = one_seg, ok2 = one_seg;    // every lane: one amp segment; moving ones: aligned, level 1 / 2
-                        if (mv.moving && one_seg) {
-                            ok1 = ok2 = (n & 31u) == 0u;
-                            if (FILTER != FILT_ONE_POLE && ok1) {
+                        bool ok = !active || n + kChunk <= F.seg_end;
+                        if (mv.moving && ok) {
+                            ok = (n & 31u) == 0u;
+                            if (FILTER != FILT_ONE_POLE && ok) {
                                 make_window_inl<FILTER>(W, sm, mv.cp, n);
-                                ok1 = W.valid == 1u;
-                                ok2 = W.valid == 2u;
-                            } else if (FILTER == FILT_ONE_POLE) {
-                                ok2 = false;
+                                ok = W.valid == 2u;
                             }
                         }
-                        if (a.force_path == 0u) {
-                            if (__all_sync(0xffffffffu, ok2) && FILTER != FILT_ONE_POLE) packed = 2;
-                            else if (__all_sync(0xffffffffu, ok1)) packed = 1;
-                        }
+                        packed = a.force_path == 0u && __all_sync(0xffffffffu, ok);
                     }
                     if (packed) {
                         if constexpr (kPackable) {
-                            constexpr bool kCanInterp = FILTER != FILT_ONE_POLE;
-                            auto run = [&](auto kind_tag) {
-                                constexpr int K = decltype(kind_tag)::value;
-                                if (packed == 1) {
-                                    if (any_resting) chunk_modcut_pk<FILTER, K, true, false, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
-                                    else chunk_modcut_pk<FILTER, K, false, false, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
-                                } else if constexpr (kCanInterp) {
-                                    if (fasthash) chunk_modcut_pk<FILTER, K, false, true, true, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
-                                    else chunk_modcut_pk<FILTER, K, false, true, false, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab);
-                                }
-                            };
                             switch (wkind) {
-                            case 0: run(std::integral_constant<int, 0>{}); break;
-                            case 1: run(std::integral_constant<int, 1>{}); break;
-                            default: run(std::integral_constant<int, -1>{}); break;
+                            case 0: chunk_modcut_pk<FILTER, 0, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                            case 1: chunk_modcut_pk<FILTER, 1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                            default: chunk_modcut_pk<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
                             }
                         }
                     } else {

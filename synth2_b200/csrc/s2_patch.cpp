@@ -192,7 +192,7 @@ struct Parser {
                     if (g == "freq") {
                         if (!number("lpf.freq", 0.0, 1e6, &v.lpf_freq_hz)) return false;
                     } else if (g == "damping") {
-                        if (!number("lpf.damping", 0.0, 10.0, &v.damping)) return false;        // Unipolar<10>, dsp_filters.rs:95
+                        if (!number("lpf.damping", 0.0, 10.0, &v.damping)) return false;        // Unipolar<10>, dsp_filters.rs:95 (> 0 for the second-order kinds: s2_synth_set_patch)
                     } else if (g == "kind") {
                         if (t.kind != Tok::Name) return err("lpf.kind: expected one_pole or biquad");
                         if (t.text == "one_pole") out->filter_kind = S2_FILTER_ONE_POLE;
