@@ -368,3 +368,125 @@ def test_host_tuned_baseline_build_gives_the_same_bits():
     finally:
         oracle.SO, oracle._lib = so, handle
     assert outs[0] == outs[2] and outs[1] == outs[3]
+
+
+# ---- one whole x16 block, restated independently in numpy float32 ------------------------------------------
+
+def _libm_f32(name):
+    import ctypes
+    import ctypes.util
+    fn = getattr(ctypes.CDLL(ctypes.util.find_library("m")), name)
+    fn.restype = ctypes.c_float
+    return fn
+
+
+def _x16_block_numpy(cfg, state, pitch, sr, offset, release):
+    """process_layer_x16 (process.rs:88-99, 137-174, 306-379) for the saw oscillator and the one-pole low-pass,
+    written from the Rust source with numpy float32 vectors — every operation a separately rounded binary32
+    operation, in the source's order — and NOT from oracle/s2_oracle.c.  Transcendentals are libm's (the oracle's
+    stand-in for sleef `pow` and Rust's `exp`).  Returns the 16 samples and advances `state` (phase, has_phase, last)."""
+    import ctypes
+    powf, expf = _libm_f32("powf"), _libm_f32("expf")
+    powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    expf.argtypes = [ctypes.c_float]
+    F = np.float32
+    srf = F(sr)
+
+    def ms(x):                                            # units.rs:44-53
+        return F(srf * F(F(x) / F(1000.0)))
+
+    def adsr(env, offs):                                  # old/simdtest.rs:270-330
+        A, D, S, R = ms(env["attack"]), ms(env["decay"]), F(env["sustain"]), ms(env["release"])
+        x = offs.astype(np.float32)
+        sus_off = F(A + D)
+        rel = np.float32(np.uint32(release)) if release != NONE else F(np.uint32(0xFFFFFFFF))
+        rel = np.maximum(rel, sus_off)
+        end = F(rel + R)
+        in_a = x < A
+        in_d = ~in_a & (x < sus_off)
+        in_s = ~in_a & ~in_d & (x < rel)
+        in_r = ~in_a & ~in_d & ~in_s & (x < end)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            line = lambda rise, run, xx, y0: (F(F(rise) / F(run)) * xx).astype(np.float32) + F(y0)   # never fused (:247-261)
+            a_s = line(1.0, A, x, 0.0)
+            d_s = line(F(S - F(1.0)), D, (x - A).astype(np.float32), 1.0)
+            r_s = line(F(-S), R, (x - rel).astype(np.float32), S)
+        out = np.zeros(16, np.float32)
+        out = np.where(in_a, a_s, out)
+        out = np.where(in_d, d_s, out)
+        out = np.where(in_s, S, out)
+        out = np.where(in_r, r_s, out)
+        return out.astype(np.float32)                     # in_end selects 0
+
+    offs = np.arange(offset, offset + 16, dtype=np.uint32)
+    gains = adsr(cfg["amp_env"], offs)
+    mods = adsr(cfg["mod_env"], offs)
+
+    def modulate(freq, amount):                           # process.rs:231-250
+        e = (mods * F(amount)).astype(np.float32)
+        return np.array([F(F(powf(2.0, float(v))) * F(freq)) for v in e], dtype=np.float32)
+
+    osc_f = modulate(pitch, cfg["mod_env_to_osc_freq"])
+    lpf_f = modulate(cfg["lpf_freq"], cfg["mod_env_to_lpf_freq"])
+    periods = (srf / osc_f).astype(np.float32)            # units.rs:32-41
+    # accum_phase_x16 (oscillators.rs:389-400): phases of the 16 frames, then the carried one
+    ph = F(state["phase"]) if state["has_phase"] else F(0.0)          # process.rs:316 unwrap_or(0)
+    phases = np.zeros(16, np.float32)
+    acc = ph
+    for i in range(16):
+        phases[i] = acc
+        acc = F(np.fmod(F(acc + F(F(1.0) / periods[i])), F(1.0)))      # (phase + 1/period) % 1.0
+    state["phase"], state["has_phase"] = acc, 1
+    # phased_offset_x16 with feature "fma": period.mul_add(phase, 0) (oscillators.rs:217-239), then % period (:105)
+    x = np.array([F(np.float64(periods[i]) * np.float64(phases[i])) for i in range(16)], dtype=np.float32)   # exact product, one rounding
+    x = np.fmod(x, periods).astype(np.float32)
+    # saw: line_y_value_with_y_offset_x16(-2, period, x, 1) with fma (math.rs:27-40): slope.mul_add(x, 1)
+    slope = (F(-2.0) / periods).astype(np.float32)
+    saw = np.array([F(np.float64(slope[i]) * np.float64(x[i]) + 1.0) for i in range(16)], dtype=np.float32)
+    osc = (saw + F(cfg["osc_gain"])).astype(np.float32)   # ADDED on the x16 path (process.rs:341-345)
+    # hash noise (hashnoise.rs:33-68) at offsets cast u32 -> f32 -> u32
+    seed = np.uint32(state["noise_seed"])
+    rot = np.uint32((int(seed) << 5 | int(seed) >> 27) & 0xFFFFFFFF)
+    o32 = offs.astype(np.float32).astype(np.uint32)
+    h = ((rot ^ o32).astype(np.uint64) * np.uint64(0x9E3779B9)) & np.uint64(0xFFFFFFFF)
+    v = (h & np.uint64(0xFFFF)).astype(np.float32)
+    nz = ((v / F(65535.0)).astype(np.float32) * F(2.0) - F(1.0)).astype(np.float32)
+    nz = (nz + F(cfg["noise"])).astype(np.float32)
+    u = (osc + nz).astype(np.float32)
+    # one-pole per frame (filters.rs:15-34): k = exp(-2 pi f / sr); y = (1 - k).mul_add(x, k * last)
+    out = np.zeros(16, np.float32)
+    last = F(state["lpf_last"])
+    for i in range(16):
+        t = F(F(F(F(-2.0) * F(np.pi)) * lpf_f[i]) / srf)
+        k = F(expf(float(t)))
+        a0 = F(F(1.0) - k)
+        last = F(np.float64(a0) * np.float64(u[i]) + np.float64(F(k * last)))       # fma: exact product + rounded k*last, one rounding
+        out[i] = last
+    state["lpf_last"] = last
+    return (out * gains).astype(np.float32)
+
+
+@pytest.mark.parametrize("release", [NONE, 4800])
+def test_whole_x16_blocks_match_an_independent_numpy_restatement(release):
+    """*derived*: the default patch (saw, one-pole, mod envelope opening the cutoff by 10 octaves; synth.rs:125-152)
+    rendered block by block through attack, decay, the cutoff sweep, sustain and release — the oracle's
+    s2o_process_layer_x16 against a restatement of process.rs written in numpy float32, bit for bit."""
+    cfg = oracle.default_config()
+    c = cfg[0]
+    assert c["osc_kind"] == 1 and c["filter_kind"] == 0
+    pitch, sr = 440.0, 48000
+    st_o = np.zeros(1, dtype=oracle.LAYER_STATE)
+    st_n = {"phase": np.float32(0), "has_phase": 0, "lpf_last": np.float32(0), "noise_seed": 0}
+    cfg_n = {"osc_gain": c["osc_gain"], "noise": c["noise"], "lpf_freq": c["lpf_freq"],
+             "mod_env_to_osc_freq": c["mod_env_to_osc_freq"], "mod_env_to_lpf_freq": c["mod_env_to_lpf_freq"],
+             "amp_env": {"attack": c["amp_env"]["attack_ms"], "decay": c["amp_env"]["decay_ms"],
+                         "sustain": c["amp_env"]["sustain"], "release": c["amp_env"]["release_ms"]},
+             "mod_env": {"attack": c["mod_env"]["attack_ms"], "decay": c["mod_env"]["decay_ms"],
+                         "sustain": c["mod_env"]["sustain"], "release": c["mod_env"]["release_ms"]}}
+    out_o = np.zeros(16, dtype=np.float32)
+    blocks = list(range(0, 12000, 16))                    # attack, decay and the whole 200 ms sweep, sustain, release
+    for off in blocks:
+        L.s2o_process_layer_x16(cfg.ctypes.data, st_o.ctypes.data, pitch, sr, off, release, out_o.ctypes.data)
+        out_n = _x16_block_numpy(cfg_n, st_n, pitch, sr, off, release)
+        assert out_o.tobytes() == out_n.tobytes(), f"block at offset {off}: {out_o} vs {out_n}"
+        assert np.float32(st_o["phase"][0]).tobytes() == np.float32(st_n["phase"]).tobytes()
