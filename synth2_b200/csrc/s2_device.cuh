@@ -728,55 +728,38 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
     };
     float2 qP = splat2(0.0f), coP = splat2(0.0f);
     float q0 = 0.0f, co0 = 0.0f;
-    float2 xc2 = xf2;                  // frame offsets of the pair whose coefficients are computed next
-    // The coefficients of trip j + 1 are computed while trip j runs its filter (software pipeline by hand: the
-    // coefficient chain is ~8 dependent packed operations per pair and feeds the filter recurrence, which is serial;
-    // one trip ahead the two are independent and the scheduler can interleave them).
-    auto coefs = [&](int j, float2 (&c0)[2], float2 (&c1)[2], float2 (&c2)[2]) {
-        float dq = 0.0f, dco = 0.0f;
-        if (INTERP) {
-            // frames [4j, 4j + 4): from node 4j (q0, co0) to node 4j + 4 — the second of the pair evaluated one trip
-            // ago on even trips, the first of the pair evaluated now (frames 4j + 4, 4j + 8) on odd ones
-            if (j & 1) nodes(__fadd_rn(xc2.x, 4.0f), &qP, &coP);
-            const float q1 = (j & 1) ? qP.x : qP.y, co1 = (j & 1) ? coP.x : coP.y;
-            dq = __fmul_rn(__fsub_rn(q1, q0), 0.25f);
-            dco = __fmul_rn(__fsub_rn(co1, co0), 0.25f);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (INTERP) {
-                const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
-                s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(q0)), pfma2(j2, splat2(dco), splat2(co0)),
-                                                                         one, &c0[h], &c1[h], &c2[h]);
-            } else {
-                c0[h] = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(mod2(xc2), mv.cp.amt, mv.cp.theta0));
-                c1[h] = pfma2(c0[h], splat2(-one), splat2(1.0f));         // 1 - k, one rounding (exact product)
-                c2[h] = splat2(0.0f);
-                if (!mv.moving) { c0[h] = splat2(F.c0); c1[h] = splat2(F.c1); }
-            }
-            xc2 = padd2(xc2, splat2(2.0f));
-        }
-        if (INTERP) {
-            q0 = (j & 1) ? qP.x : qP.y;
-            co0 = (j & 1) ? coP.x : coP.y;
-        }
-    };
     if (INTERP) {
         nodes(xf2.x, &qP, &coP);       // frames n0 and n0 + 4
         q0 = qP.x; co0 = coP.x;
     }
-    float2 a0[2], a1[2], a2[2];        // coefficients of the current trip
-    coefs(0, a0, a1, a2);
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
-        float2 b0[2], b1[2], b2[2];    // ... of the next one (the last trip computes a set nobody uses)
-        coefs(j + 1, b0, b1, b2);
+        float dq = 0.0f, dco = 0.0f;
+        if (INTERP) {
+            // frames [4j, 4j + 4): from node 4j (q0, co0) to node 4j + 4 — the second of the pair evaluated one trip
+            // ago on even trips, the first of the pair evaluated now (frames 4j + 4, 4j + 8) on odd ones
+            if (j & 1) nodes(__fadd_rn(xf2.x, 4.0f), &qP, &coP);
+            const float q1 = (j & 1) ? qP.x : qP.y, co1 = (j & 1) ? coP.x : coP.y;
+            dq = __fmul_rn(__fsub_rn(q1, q0), 0.25f);
+            dco = __fmul_rn(__fsub_rn(co1, co0), 0.25f);
+        }
         float o4[4];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            float2 c0, c1, c2;
+            if (INTERP) {
+                const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
+                s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(q0)), pfma2(j2, splat2(dco), splat2(co0)),
+                                                                         one, &c0, &c1, &c2);
+            } else {
+                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(mod2(xf2), mv.cp.amt, mv.cp.theta0));
+                c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
+                c2 = splat2(0.0f);
+                if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); }
+            }
             FiltC ca, cb;
-            ca.c0 = a0[h].x; ca.c1 = a1[h].x; ca.c2 = a2[h].x;
-            cb.c0 = a0[h].y; cb.c1 = a1[h].y; cb.c2 = a2[h].y;
+            ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
+            cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
             const float pa = ph;
             const float pb = wrap_unit(__fadd_rn(pa, F.d));
             ph = wrap_unit(__fadd_rn(pb, F.d));
@@ -793,8 +776,10 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
             xf2 = padd2(xf2, splat2(2.0f));
         }
         *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-#pragma unroll
-        for (int h = 0; h < 2; h++) { a0[h] = b0[h]; a1[h] = b1[h]; a2[h] = b2[h]; }
+        if (INTERP) {
+            q0 = (j & 1) ? qP.x : qP.y;
+            co0 = (j & 1) ? coP.x : coP.y;
+        }
     }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;

@@ -8,6 +8,11 @@
 //     then takes AT MOST ONE new filled buffer without blocking, writes every sample to all output channels,
 //     and pads what is left with zeros (an underrun is logged, never waited for); a drained buffer goes back
 //     to the synth thread (audio_player.rs:205-255).
+// The audio side takes no lock, as the reference's does not (`try_recv` / `send` on channels of depth 2): buffers
+// travel through two single-producer / single-consumer rings of atomics, the synth thread's error state is an atomic
+// flag, and the only thing the callback does beyond loads and stores is a condition-variable notify (no mutex held).
+// The synth thread sleeps on that condition variable with a 1 ms timeout, so a notify that races its check costs at
+// most a millisecond of a 42.7 ms buffer.
 // The reference polls MIDI between 16-frame chunks while it fills a buffer (main.rs:138-147); a buffer
 // renders here in microseconds, so messages are applied once, before the buffer is rendered.
 #include "../../include/s2_cuda.h"
@@ -33,6 +38,27 @@ constexpr size_t kFrames = S2_PLAYER_BUFFER_FRAMES;
 constexpr int kBuffers = 2;            // sync_channel(2) each way, two buffers in circulation
 
 struct Msg { uint8_t note; uint8_t on; float velocity; };
+
+// Single-producer / single-consumer ring of buffer indices (capacity 4 >= the two buffers in circulation).
+struct Ring {
+    std::atomic<uint32_t> head{0}, tail{0};      // pop at head, push at tail
+    int slot[4] = {};
+    bool push(int v) {                           // producer only
+        const uint32_t t = tail.load(std::memory_order_relaxed);
+        if (t - head.load(std::memory_order_acquire) == 4u) return false;
+        slot[t & 3u] = v;
+        tail.store(t + 1u, std::memory_order_release);
+        return true;
+    }
+    bool pop(int* v) {                           // consumer only
+        const uint32_t h = head.load(std::memory_order_relaxed);
+        if (h == tail.load(std::memory_order_acquire)) return false;
+        *v = slot[h & 3u];
+        head.store(h + 1u, std::memory_order_release);
+        return true;
+    }
+    bool empty() const { return head.load(std::memory_order_acquire) == tail.load(std::memory_order_acquire); }
+};
 }  // namespace
 
 struct s2_player {
@@ -40,15 +66,16 @@ struct s2_player {
     uint32_t sample_rate = 0;
     s2_synth* synth = nullptr;
     float* buf[kBuffers] = {};         // pinned host memory
-    // producer (synth thread) <-> consumer (audio callback): indices of buffers, FIFO each way
-    std::mutex mu;
+    // synth thread <-> audio callback: indices of buffers, FIFO each way, lock-free
+    Ring empty_q;                      // callback -> synth thread
+    Ring filled_q;                     // synth thread -> callback
+    std::mutex mu;                     // control side only (note messages, start / stop, waiters): never the callback
     std::condition_variable cv_empty, cv_progress;
-    std::vector<int> empty_q, filled_q;
     std::vector<Msg> inbox;            // note messages not yet applied
     bool started = false, stop = false;
-    int failed = 0;                    // error code of the synth thread, sticky
+    std::atomic<int> failed{0};        // error code of the synth thread, sticky; fail_msg is written before it is set
     std::string fail_msg;
-    uint64_t rendered = 0;             // buffers handed over filled
+    std::atomic<uint64_t> rendered{0}; // buffers handed over filled
     std::thread worker;
     // consumer-only state (the callback thread)
     int pending = -1;                  // buffer being drained
@@ -64,10 +91,12 @@ void synth_thread(s2_player* p) {
         std::vector<Msg> msgs;
         {
             std::unique_lock<std::mutex> lk(p->mu);
-            p->cv_empty.wait(lk, [&] { return p->stop || (p->started && !p->empty_q.empty()); });
+            // the callback pushes into empty_q and notifies WITHOUT this mutex: poll at 1 ms so a notify that
+            // slips between the check and the wait is not waited for
+            while (!(p->stop || (p->started && !p->empty_q.empty())))
+                p->cv_empty.wait_for(lk, std::chrono::milliseconds(1));
             if (p->stop) return;
-            b = p->empty_q.front();
-            p->empty_q.erase(p->empty_q.begin());
+            p->empty_q.pop(&b);
             msgs.swap(p->inbox);
         }
         int rc = S2_OK;
@@ -76,15 +105,20 @@ void synth_thread(s2_player* p) {
             if (rc < 0) break;
         }
         if (rc >= 0) rc = s2_synth_sample(p->synth, p->buf[b], kFrames, p->sample_rate);
-        std::lock_guard<std::mutex> lk(p->mu);
         if (rc < 0) {
-            p->failed = rc;
-            p->fail_msg = s2_last_error();
+            {
+                std::lock_guard<std::mutex> lk(p->mu);
+                p->fail_msg = s2_last_error();
+                p->failed.store(rc, std::memory_order_release);
+            }
             p->cv_progress.notify_all();
             return;
         }
-        p->filled_q.push_back(b);
-        p->rendered++;
+        p->filled_q.push(b);
+        {
+            std::lock_guard<std::mutex> lk(p->mu);       // pairs with the waiters of s2_player_wait_buffers
+            p->rendered.fetch_add(1, std::memory_order_release);
+        }
         p->cv_progress.notify_all();
     }
 }
@@ -98,11 +132,10 @@ size_t fill_from_pending(s2_player* p, float* out, size_t frames, uint32_t chann
         for (uint32_t c = 0; c < channels; c++) out[i * channels + c] = src[i];
     p->consumed += n;
     if (p->consumed == kFrames) {
-        std::lock_guard<std::mutex> lk(p->mu);
-        p->empty_q.push_back(p->pending);
+        p->empty_q.push(p->pending);               // lock-free; two buffers never overfill a ring of four
         p->pending = -1;
         p->consumed = 0;
-        p->cv_empty.notify_one();
+        p->cv_empty.notify_one();                  // no mutex: see synth_thread
     }
     return n;
 }
@@ -130,7 +163,7 @@ int s2_player_new(int device, uint32_t sample_rate, s2_player** out) {
             return s2::set_error(S2_ERR_NOMEM, "cudaMallocHost failed for the player buffers");
         }
         memset(p->buf[i], 0, kFrames * sizeof(float));       // Buffer(Box::from([0_f32; BUFFER_FRAMES]))
-        p->empty_q.push_back(i);
+        p->empty_q.push(i);
     }
     p->worker = std::thread(synth_thread, p);
     *out = p;
@@ -171,7 +204,7 @@ int s2_player_start(s2_player* p) {
 static int post(s2_player* p, uint8_t note, uint8_t on, float velocity) {
     if (!p) return s2::set_error(S2_ERR_INVALID, "null player");
     std::lock_guard<std::mutex> lk(p->mu);
-    if (p->failed) return s2::set_error(p->failed, "synth thread: %s", p->fail_msg.c_str());
+    if (const int f = p->failed.load(std::memory_order_acquire)) return s2::set_error(f, "synth thread: %s", p->fail_msg.c_str());
     p->inbox.push_back({note, on, velocity});
     return S2_OK;
 }
@@ -185,12 +218,9 @@ int64_t s2_player_fill(s2_player* p, float* out, size_t frames, uint32_t channel
     if (channels == 0) return s2::set_error(S2_ERR_INVALID, "channels must be > 0");
     size_t written = fill_from_pending(p, out, frames, channels);
     if (written < frames) {
-        int got = -1, failed = 0;
-        {
-            std::lock_guard<std::mutex> lk(p->mu);       // try_recv
-            if (!p->filled_q.empty()) { got = p->filled_q.front(); p->filled_q.erase(p->filled_q.begin()); }
-            failed = p->failed;
-        }
+        int got = -1;
+        if (!p->filled_q.pop(&got)) got = -1;            // try_recv: lock-free
+        const int failed = p->failed.load(std::memory_order_acquire);
         if (got >= 0) {
             p->pending = got;
             p->consumed = 0;
@@ -199,10 +229,7 @@ int64_t s2_player_fill(s2_player* p, float* out, size_t frames, uint32_t channel
             p->underruns.fetch_add(1, std::memory_order_relaxed);   // "didn't receive buffer in time for audio out"
         }
         memset(out + written * channels, 0, (frames - written) * channels * sizeof(float));
-        if (got < 0 && failed) {
-            std::lock_guard<std::mutex> lk(p->mu);
-            return s2::set_error(failed, "synth thread: %s", p->fail_msg.c_str());
-        }
+        if (got < 0 && failed) return s2::set_error(failed, "synth thread: %s", p->fail_msg.c_str());   // written before `failed`
     }
     p->frames_played.fetch_add(written, std::memory_order_relaxed);
     return (int64_t)written;
@@ -210,8 +237,7 @@ int64_t s2_player_fill(s2_player* p, float* out, size_t frames, uint32_t channel
 
 int s2_player_stats(s2_player* p, uint64_t* buffers_rendered, uint64_t* underruns, uint64_t* frames_played) {
     if (!p) return s2::set_error(S2_ERR_INVALID, "null player");
-    std::lock_guard<std::mutex> lk(p->mu);
-    if (buffers_rendered) *buffers_rendered = p->rendered;
+    if (buffers_rendered) *buffers_rendered = p->rendered.load(std::memory_order_acquire);
     if (underruns) *underruns = p->underruns.load(std::memory_order_relaxed);
     if (frames_played) *frames_played = p->frames_played.load(std::memory_order_relaxed);
     return S2_OK;
@@ -221,8 +247,8 @@ int s2_player_wait_buffers(s2_player* p, uint64_t n_rendered, uint32_t timeout_m
     if (!p) return s2::set_error(S2_ERR_INVALID, "null player");
     std::unique_lock<std::mutex> lk(p->mu);
     const bool ok = p->cv_progress.wait_for(lk, std::chrono::milliseconds(timeout_ms),
-                                            [&] { return p->failed || p->rendered >= n_rendered; });
-    if (p->failed) return s2::set_error(p->failed, "synth thread: %s", p->fail_msg.c_str());
+                                            [&] { return p->failed.load(std::memory_order_acquire) || p->rendered.load(std::memory_order_acquire) >= n_rendered; });
+    if (const int f = p->failed.load(std::memory_order_acquire)) return s2::set_error(f, "synth thread: %s", p->fail_msg.c_str());
     return ok ? S2_OK : 1;
 }
 

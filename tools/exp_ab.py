@@ -26,7 +26,11 @@ for rep in range(2):
 print(json.dumps(res))
 '''
 for lib in sys.argv[1:]:
+    lib, _, extra = lib.partition(":")                   # lib.so:VAR=value sets an environment variable for that run
     env = dict(os.environ, S2_LIB=os.path.abspath(lib), PYTHONPATH=".")
+    if extra:
+        k, _, v = extra.partition("=")
+        env[k] = v
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:]
-    print(f"{os.path.basename(lib):28s} {line}", flush=True)
+    print(f"{os.path.basename(lib) + ' ' + extra:40s} {line}", flush=True)
