@@ -289,6 +289,34 @@ from synth2_b200 import patch as s2patch
 EXAMPLE_SYNTH2 = "synth mySynth {\n\n}\n"          # the reference's example.synth2, verbatim
 
 
+def test_moving_cutoff_functions_on_cpu(tmp_path):
+    """synth2_b200/csrc/s2_cutoff.h compiles for the CPU: the straight-line division, e^-theta, the windowed
+    sin / cos, a whole decay sweep at the worst corner and the 8-frame interpolation (tools/check_cutoff.cpp)."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    exe = tmp_path / "check_cutoff"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-march=x86-64-v3", "-o", str(exe),
+                    str(ROOT / "tools" / "check_cutoff.cpp")], check=True, capture_output=True)
+    res = subprocess.run([str(exe), "quick"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.strip().endswith("ok")
+
+
+def test_bench_reference_arm_never_loads_the_product_library():
+    """VERDICT r1 #10: `bench.py --impl reference` is the CPU port alone; libs2cuda.so must not be mapped."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LD_DEBUG="files")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0
+    assert "libs2cuda" not in res.stderr and "libs2cuda" not in res.stdout
+    assert '"impl": "reference"' in res.stdout
+
+
 def test_patch_example_is_the_default_patch():
     p = s2patch.parse(EXAMPLE_SYNTH2)
     assert p.name == "mySynth" and p.filter_kind == s2.FILTER_ONE_POLE and p.events.size == 0

@@ -169,6 +169,50 @@ int main(int argc, char** argv) {
         // calls, differ from the rounded-once values in 1.3 % of arguments)
         fail |= coef_diff * 1000 > frames;
     }
+    // ---- 5. interpolation: (q, cos) at the frames of the grid of 8, linear in between, against the window evaluation of
+    //         every frame — relative difference of c0 = 2 alpha (the coefficient that cancels) at the bench bank's sweep
+    //         rate and at the rate limit kInterpRate12
+    for (int pass = 0; pass < 2; pass++) {
+        const float sr = 48000.0f, one = 1.0f;
+        const float amt = 1.5f, D = pass == 0 ? 9600.0f : 1.5f * 12.0f / (kInterpRate12 * 1.0001f);      // 12 |amt es| at the limit
+        const float sD = (0.0f - 1.0f) / D;
+        double worst_rel = 0.0, worst_abs = 0.0, bias_sum = 0.0;
+        long bias_n = 0;
+        for (int voice = 0; voice < 24; voice++) {
+            const float lpf = 100.0f * powf(80.0f, (float)voice / 23.0f), hd = 0.1f + 0.026f * (float)voice;
+            const float th0 = (kTwoPi * lpf) / sr;
+            const uint32_t frames = (uint32_t)D & ~31u;
+            for (uint32_t w0 = 0; w0 + 32 <= frames; w0 += 32) {
+                Window W;
+                const float xc = (float)(w0 + 16u);
+                make_window(W, theta_at<float>((sD * (xc - 0.0f)) + 1.0f, amt, th0));
+                if (!(W.thc <= kThetaMax)) continue;
+                for (uint32_t k = w0; k < w0 + 32; k += 8) {
+                    float qa, ca, qb, cb;
+                    node_q_cos<float>(W, (sD * (float)k) + 1.0f, amt, th0, hd, one, &qa, &ca);
+                    node_q_cos<float>(W, (sD * (float)(k + 8)) + 1.0f, amt, th0, hd, one, &qb, &cb);
+                    const float dq = (qb - qa) * 0.125f, dc = (cb - ca) * 0.125f;
+                    for (uint32_t j = 0; j < 8; j++) {
+                        float a0, a1, a2, b0, b1, b2, q, co;
+                        biquad_from_q_cos<false, float>(fmaf((float)j, dq, qa), fmaf((float)j, dc, ca), one, &a0, &a1, &a2);
+                        node_q_cos<float>(W, (sD * (float)(k + j)) + 1.0f, amt, th0, hd, one, &q, &co);
+                        biquad_from_q_cos<false, float>(q, co, one, &b0, &b1, &b2);
+                        const double rel = fabs((double)a0 - (double)b0) / fabs((double)b0);
+                        if (rel > worst_rel) worst_rel = rel;
+                        if (lpf < 250.0f) { bias_sum += ((double)a0 - (double)b0) / (double)b0; bias_n++; }
+                        const double ab = fmax(fabs((double)a1 - (double)b1), fabs((double)a2 - (double)b2));
+                        if (ab > worst_abs) worst_abs = ab;
+                    }
+                }
+            }
+        }
+        // the per-frame evaluation itself scatters by ~2^-25 / alpha in c0 (the cancellation: ~7e-4 at 100 Hz); what the
+        // interpolation may add is a BIAS of (8 ln2 |amt es|)^2 / 2 at most — the mean over the low cutoffs shows it
+        const double bias = bias_n ? bias_sum / (double)bias_n : 0.0;
+        printf("interpolation (%s): c0 relative difference worst %.2e (scatter of the cancellation), mean at cutoffs < 250 Hz %+.2e; "
+               "c1 / c2 absolute difference worst %.2e\n", pass == 0 ? "1.5 octaves in 200 ms" : "rate limit", worst_rel, bias, worst_abs);
+        fail |= worst_abs > (pass == 0 ? 4e-6 : 6e-5) || worst_rel > 2e-3 || fabs(bias) > (pass == 0 ? 2e-6 : 2e-5);
+    }
     printf(fail ? "FAILED\n" : "ok\n");
     return fail;
 }
