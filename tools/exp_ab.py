@@ -23,7 +23,19 @@ for rep in range(2):
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(40)]
     res = {"first20_ms": sum(ms[:20]), "modcut3": sum(ms[:3]), "ramp_3_12": sum(ms[3:12]), "sustain_avg": sum(ms[24:40]) / 16}
-print(json.dumps(res))
+bank.close()
+# the latency-bound regime: half the voices (1.7 warps per scheduler), sustain
+vh = voices[:V // 2]
+bank = s2.VoiceBank(vh, SR, 1, device=0, stream=stream)
+bank.set_pipeline(4)
+for i in range(16): bank.render(T, ring[i & 1][:V // 2], T, None)
+bank.join(stream); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+for i in range(40): bank.render(T, ring[i & 1][:V // 2], T, None)
+bank.join(stream); e1.record(stream); torch.cuda.synchronize()
+res["half_bank_sustain"] = e0.elapsed_time(e1) / 40
+print(json.dumps({k: round(v, 4) for k, v in res.items()}))
 '''
 for lib in sys.argv[1:]:
     lib, _, extra = lib.partition(":")                   # lib.so:VAR=value sets an environment variable for that run
