@@ -171,10 +171,10 @@ S2C_FN T exp_neg_fast(T th) {
 struct Window {
     uint32_t k;             // window index (frame offset >> 5); 0xffffffff = none yet
     uint32_t valid;         // 0: frames of this window take the full evaluation; 1: window evaluation per frame;
-                            // 2: window evaluation at every 8th frame, linear in between (see kInterpRate12)
+                            // 2: window evaluation at every 4th frame, linear in between (see kInterpRate)
     float thc;              // theta of the centre frame
     float Ah, Al, Bh, Bl;   // sin (A) and cos (B) of thc as hi + lo
-    // scalar form only: the interpolation interval [knode, knode + 8) last evaluated
+    // scalar form only: the interpolation interval [knode, knode + 4) last evaluated
     uint32_t knode;
     float qa, coa, dq, dco;
 };
@@ -182,13 +182,13 @@ struct Window {
 // Interpolation (second-order filters).  q = (1 - h) / (1 + h), h = damping/2 * sin(theta), and cos(theta) are smooth
 // in the frame offset; the algebra that turns them into (alpha, beta, gamma) is where the reference's rounding lives
 // (alpha = (1/2 + beta - gamma) / 4 cancels).  So q and cos are evaluated through the window at the frames of an
-// absolute grid of 8 and taken linear in between, and the coefficient algebra runs per frame on them exactly as the
+// absolute grid of 4 and taken linear in between, and the coefficient algebra runs per frame on them exactly as the
 // reference's does.  Linear interpolation of cos over an interval of d radians is off by at most d^2 / 8; with the
-// angle moving by the factor 2^(amt * es) per frame, d = 8 ln2 |amt es| theta, which makes the relative error of
-// alpha (~theta^2 / 4 at low cutoffs, the sensitive end) (8 ln2 |amt es|)^2 / 2: 3.7e-7 for the bench bank's sweep
-// (1.5 octaves in 200 ms), at most 8e-6 at the rate limit below (7 octaves in 200 ms) — against the 2e-4 by which
-// the reference's own binary32 alpha scatters from frame to frame at 100 Hz.  Faster sweeps evaluate every frame.
-constexpr float kInterpRate12 = 0.0086f;      // 12 |amt es| <= this
+// angle moving by the factor 2^(amt * es) per frame, d = 4 ln2 |amt es| theta, which makes the relative error of
+// alpha (~theta^2 / 4 at low cutoffs, the sensitive end) (4 ln2 |amt es|)^2 / 2: 9e-8 for the bench bank's sweep
+// (1.5 octaves in 200 ms), 4.2e-6 for the default patch's (10 octaves in 200 ms) — against the 2e-4 by which the
+// reference's own binary32 alpha scatters from frame to frame at 100 Hz.  Faster sweeps evaluate every frame.
+constexpr float kInterpRate12 = 0.0135f;      // 12 |amt es| <= this
 
 S2C_FN void split_hi_lo(double v, float* hi, float* lo) {
     *hi = (float)v;

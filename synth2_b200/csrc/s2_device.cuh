@@ -328,17 +328,17 @@ __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const Seg
     if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp); return; }
     if ((n >> s2c::kWinShift) != W.k) make_window<FILTER>(W, sm, cp, n);
     if (W.valid == 2u && (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP)) {
-        // q and cos at the frames of the absolute grid of 8 around n, linear in between (s2_cutoff.h)
-        const uint32_t k = n & ~7u;
+        // q and cos at the frames of the absolute grid of 4 around n, linear in between (s2_cutoff.h)
+        const uint32_t k = n & ~3u;
         if (k != W.knode) {
             float qb, cob;
             s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k)), cp.amt, cp.theta0, cp.hd, one, &W.qa, &W.coa);
-            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k + 8u)), cp.amt, cp.theta0, cp.hd, one, &qb, &cob);
-            W.dq = __fmul_rn(__fsub_rn(qb, W.qa), 0.125f);
-            W.dco = __fmul_rn(__fsub_rn(cob, W.coa), 0.125f);
+            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k + 4u)), cp.amt, cp.theta0, cp.hd, one, &qb, &cob);
+            W.dq = __fmul_rn(__fsub_rn(qb, W.qa), 0.25f);
+            W.dco = __fmul_rn(__fsub_rn(cob, W.coa), 0.25f);
             W.knode = k;
         }
-        const float j = __uint2float_rn(n & 7u);
+        const float j = __uint2float_rn(n & 3u);
         s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float>(__fmaf_rn(j, W.dq, W.qa), __fmaf_rn(j, W.dco, W.coa), one,
                                                                 &c.c0, &c.c1, &c.c2);
     } else if (W.valid) {
@@ -699,7 +699,7 @@ struct MovV {
 // the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every lane): the chunk lies
 // inside the lane's current amp-envelope segment (F.es .., as G_LINE); for every MOVING lane it starts at a multiple
 // of 32 frames, lies inside one segment of the mod envelope, and (second-order filters) its window W is valid at
-// level 2: q and cos at every 8th frame, linear in between, the coefficient algebra per frame (s2_cutoff.h).  The
+// level 2: q and cos at every 4th frame, linear in between, the coefficient algebra per frame (s2_cutoff.h).  The
 // one-pole evaluates k = e^-theta every frame.  Lanes whose cutoff rests run the same code: their interpolation
 // nodes are their own 2 beta and cos(theta), which the algebra turns into their resting coefficients bit for bit
 // (one-pole: they select their constants).
@@ -721,39 +721,34 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
     auto mod2 = [&](float2 x2) {      // the mod envelope's line at two frame offsets
         return s2c::vaddp(pmul2(splat2(mv.mes), padd2(x2, splat2(mv.mnex0))), splat2(mv.mey0), one);
     };
-    // nodes of the interpolation: (q, cos) at frames (x, x + 8)
+    // nodes of the interpolation: (q, cos) at frames (x, x + 4)
     auto nodes = [&](float x, float2* q, float2* co) {
-        s2c::node_q_cos<float2>(W, mod2(make_float2(x, __fadd_rn(x, 8.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, q, co);
+        s2c::node_q_cos<float2>(W, mod2(make_float2(x, __fadd_rn(x, 4.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, q, co);
         if (!mv.moving) { *q = splat2(mv.q_rest); *co = splat2(mv.co_rest); }
     };
     float2 qP = splat2(0.0f), coP = splat2(0.0f);
     float q0 = 0.0f, co0 = 0.0f;
-    float dq = 0.0f, dco = 0.0f;
-    if (INTERP) nodes(xf2.x, &qP, &coP);       // frames n0 and n0 + 8
+    if (INTERP) {
+        nodes(xf2.x, &qP, &coP);       // frames n0 and n0 + 4
+        q0 = qP.x; co0 = coP.x;
+    }
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
-        if (INTERP && (j & 1) == 0) {
-            // a new 8-frame interval [8i, 8i + 8), i = j / 2: from node 8i to node 8i + 8.  Even i: the pair in hand;
-            // odd i: its second node, then the first of the pair evaluated now (frames 8i + 8, 8i + 16)
-            float q1, co1;
-            if (j & 2) {
-                q0 = qP.y; co0 = coP.y;
-                nodes(__fadd_rn(xf2.x, 8.0f), &qP, &coP);
-                q1 = qP.x; co1 = coP.x;
-            } else {
-                q0 = qP.x; co0 = coP.x;
-                q1 = qP.y; co1 = coP.y;
-            }
-            dq = __fmul_rn(__fsub_rn(q1, q0), 0.125f);
-            dco = __fmul_rn(__fsub_rn(co1, co0), 0.125f);
+        float dq = 0.0f, dco = 0.0f;
+        if (INTERP) {
+            // frames [4j, 4j + 4): from node 4j (q0, co0) to node 4j + 4 — the second of the pair evaluated one trip
+            // ago on even trips, the first of the pair evaluated now (frames 4j + 4, 4j + 8) on odd ones
+            if (j & 1) nodes(__fadd_rn(xf2.x, 4.0f), &qP, &coP);
+            const float q1 = (j & 1) ? qP.x : qP.y, co1 = (j & 1) ? coP.x : coP.y;
+            dq = __fmul_rn(__fsub_rn(q1, q0), 0.25f);
+            dco = __fmul_rn(__fsub_rn(co1, co0), 0.25f);
         }
         float o4[4];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             float2 c0, c1, c2;
             if (INTERP) {
-                const float jb = (j & 1) ? 4.0f : 0.0f;       // frames 4..7 of the interval on odd trips
-                const float2 j2 = make_float2(jb + 2.0f * h, jb + 2.0f * h + 1.0f);
+                const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
                 s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(q0)), pfma2(j2, splat2(dco), splat2(co0)),
                                                                          one, &c0, &c1, &c2);
             } else {
@@ -781,6 +776,10 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
             xf2 = padd2(xf2, splat2(2.0f));
         }
         *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        if (INTERP) {
+            q0 = (j & 1) ? qP.x : qP.y;
+            co0 = (j & 1) ? coP.x : coP.y;
+        }
     }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;

@@ -169,7 +169,7 @@ int main(int argc, char** argv) {
         // calls, differ from the rounded-once values in 1.3 % of arguments)
         fail |= coef_diff * 1000 > frames;
     }
-    // ---- 5. interpolation: (q, cos) at the frames of the grid of 8, linear in between, against the window evaluation of
+    // ---- 5. interpolation: (q, cos) at the frames of the grid of 4, linear in between, against the window evaluation of
     //         every frame — relative difference of c0 = 2 alpha (the coefficient that cancels) at the bench bank's sweep
     //         rate and at the rate limit kInterpRate12
     for (int pass = 0; pass < 2; pass++) {
@@ -187,12 +187,12 @@ int main(int argc, char** argv) {
                 const float xc = (float)(w0 + 16u);
                 make_window(W, theta_at<float>((sD * (xc - 0.0f)) + 1.0f, amt, th0));
                 if (!(W.thc <= kThetaMax)) continue;
-                for (uint32_t k = w0; k < w0 + 32; k += 8) {
+                for (uint32_t k = w0; k < w0 + 32; k += 4) {
                     float qa, ca, qb, cb;
                     node_q_cos<float>(W, (sD * (float)k) + 1.0f, amt, th0, hd, one, &qa, &ca);
-                    node_q_cos<float>(W, (sD * (float)(k + 8)) + 1.0f, amt, th0, hd, one, &qb, &cb);
-                    const float dq = (qb - qa) * 0.125f, dc = (cb - ca) * 0.125f;
-                    for (uint32_t j = 0; j < 8; j++) {
+                    node_q_cos<float>(W, (sD * (float)(k + 4)) + 1.0f, amt, th0, hd, one, &qb, &cb);
+                    const float dq = (qb - qa) * 0.25f, dc = (cb - ca) * 0.25f;
+                    for (uint32_t j = 0; j < 4; j++) {
                         float a0, a1, a2, b0, b1, b2, q, co;
                         biquad_from_q_cos<false, float>(fmaf((float)j, dq, qa), fmaf((float)j, dc, ca), one, &a0, &a1, &a2);
                         node_q_cos<float>(W, (sD * (float)(k + j)) + 1.0f, amt, th0, hd, one, &q, &co);
@@ -207,7 +207,7 @@ int main(int argc, char** argv) {
             }
         }
         // the per-frame evaluation itself scatters by ~2^-25 / alpha in c0 (the cancellation: ~7e-4 at 100 Hz); what the
-        // interpolation may add is a BIAS of (8 ln2 |amt es|)^2 / 2 at most — the mean over the low cutoffs shows it
+        // interpolation may add is a BIAS of (4 ln2 |amt es|)^2 / 2 at most — the mean over the low cutoffs shows it
         const double bias = bias_n ? bias_sum / (double)bias_n : 0.0;
         printf("interpolation (%s): c0 relative difference worst %.2e (scatter of the cancellation), mean at cutoffs < 250 Hz %+.2e; "
                "c1 / c2 absolute difference worst %.2e\n", pass == 0 ? "1.5 octaves in 200 ms" : "rate limit", worst_rel, bias, worst_abs);
