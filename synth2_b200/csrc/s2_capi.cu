@@ -543,19 +543,15 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
         // ranges of followers (1.9x the work per frame for 200 ms) fall behind the others and finish alone on a
         // part-filled machine.  Measured on the bench bank, first 20 blocks: 6.2 ms grouped and contiguous, 7.1 ms
         // grouped and dealt over the ranges, against mixed warps (every warp pays, all ranges in step).
-        struct Key { uint32_t follows, kind; float amp_rest; };
+        struct Key { uint32_t kind; float amp_rest; };
         std::vector<Key> keys(n_voices);
-        const char* sm = getenv("S2_SORT_MODE");              // experiment hook: 1 = followers grouped, ranges contiguous
-        const bool group_followers = sm && sm[0] == '1';
         for (size_t i = 0; i < n_voices; i++) {
             const s2_voice_desc& d = voices[i];
-            const uint32_t follows = d.mod_env_to_osc_freq != 0.0f ? 2u : d.mod_env_to_lpf_freq != 0.0f ? 1u : 0u;
-            keys[i] = {group_followers ? follows : 0u, d.active ? d.osc_kind : 4u, d.amp_attack_ms + d.amp_decay_ms};
+            keys[i] = {d.active ? d.osc_kind : 4u, d.amp_attack_ms + d.amp_decay_ms};
         }
         std::stable_sort(b->voice_of_slot.begin(), b->voice_of_slot.end(), [&](uint32_t x, uint32_t y) {
             const Key& a = keys[x];
             const Key& c = keys[y];
-            if (a.follows != c.follows) return a.follows < c.follows;
             if (a.kind != c.kind) return a.kind < c.kind;
             return a.amp_rest < c.amp_rest;
         });
@@ -563,7 +559,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
         // eighth / quarter / half of the slot range — the voice ranges of s2_bank_set_pipeline — then holds the same
         // mix of kinds and envelope lengths, so the ranges' streams advance together.
         const size_t full_warps = n_voices / 32;
-        if (full_warps >= 16 && !group_followers) {
+        if (full_warps >= 16) {
             std::vector<uint32_t> dealt;
             dealt.reserve(n_voices);
             for (size_t bin = 0; bin < 8; bin++)

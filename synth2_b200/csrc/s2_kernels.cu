@@ -195,7 +195,7 @@ render_kernel(const RenderArgs a) {
     // those are sustain / end stages; semi_left: frames for which the moving-cutoff classification holds.
     // 0 = look again before the next chunk.
     uint32_t fast_left = 0, seg_left = 0, semi_left = 0;
-    bool all_gconst = false, any_resting = false;
+    bool all_gconst = false;
 
     // Runs of tiles.  A third of the warp's stall time sits at the tile boundaries (loop control, dispatch,
     // store-variant selection: uniform-datapath code with exposed latencies, and the warps of an SM reach it in
@@ -319,10 +319,7 @@ render_kernel(const RenderArgs a) {
                 warp_semi = !warp_fast && amask != 0u && __all_sync(0xffffffffu, lane_semi);
                 fast_left = semi_left = 0;
                 if (warp_fast) fast_left = __reduce_min_sync(0xffffffffu, lane_left);
-                if (warp_semi) {
-                    semi_left = __reduce_min_sync(0xffffffffu, lane_left);
-                    any_resting = __any_sync(0xffffffffu, active && lane_fast);
-                }
+                if (warp_semi) semi_left = __reduce_min_sync(0xffffffffu, lane_left);
             }
 
             if (warp_fast) {

@@ -768,7 +768,7 @@ def test_sweep_variants_config5():
     assert_state_parity(st, rst, 1)
     # full width, first block: the sample's rows come out bit-identical inside the 32,768-variant bank.  There
     # every warp is 32 detunes of one (cutoff, damping) pair, so the moving-cutoff chunks compute their
-    # coefficients once per warp, one frame per lane (chunk_modcut<SHARED>); the 64-variant sample above took the
+    # coefficients once per warp, one frame per lane (modcut_coefficients + chunk_modcut_sc<SHARED>); the 64-variant sample above took the
     # per-voice form.  Silent voices parked at another frame offset must not disturb their warp.
     idle = np.setdiff1d(np.arange(7, 32768, 32), pick)
     v["active"][idle] = 0
