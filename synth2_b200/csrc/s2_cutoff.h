@@ -2,32 +2,37 @@
 //
 // While the mod envelope ramps, the reference re-derives the filter coefficients every frame from
 // fl = 2^(m * amount) * cutoff (process.rs:146-152, 231-250; filters.rs:17-21; dsp_filters.rs:99-109).  Round 1
-// evaluated 2^x, sin and cos in binary64 per frame (~150 instructions); this file is the cheap form:
+// evaluated 2^x, sin and cos in binary64 per frame (~150 instructions); this file is the cheap form that still gives
+// the reference's BITS in all but a percent of the frames — which matters: at low cutoffs the second-order
+// low-pass's alpha = (1/2 + beta - gamma) / 4 cancels to 1e-5 and scatters by 1e-3 of itself from frame to frame
+// with the last bit of cos, so two renders whose coefficients differ in most frames drift apart by several 1e-4
+// (measured with a 2-ulp 2^x: 1 % of random banks outside the north-star bar), while rare one-ulp events do not.
 //
-//   * theta = 2 pi fl / sr = 2^(m * amount) * theta0 with theta0 = (2 pi cutoff) / sr a per-voice constant and 2^x
-//     the hardware's ex2.approx (2 ulp): theta within ~3 ulp of the reference's own chain.  The reference's sleef
-//     `pow` is itself unpinned at the ulp level, and the low-pass's DC gain does not depend on theta, so an ulp of
-//     cutoff moves the output by ~Q * 2^-23 (VERDICT r1 #1b).
-//   * sin / cos (second-order and first-order filters): frame offsets are cut into absolute windows of 32 frames
-//     [32k, 32k + 32).  Per window, theta_c of its centre frame gets the full binary64 evaluation (s2_math.h),
-//     kept as hi + lo binary32 pairs; a frame's value is the angle-addition correction in binary32 around it:
-//     sin(tc + d) = S + (C sin d - S (1 - cos d)), |d| <= 2^-7 so sin d = d - d^3/6 and 1 - cos d = d^2/2 to
-//     2e-10.  Absolute error <= ~1e-9 beyond a correct rounding, unbiased — which is what the second-order
-//     low-pass needs: alpha = (1/2 + beta - gamma)/4 cancels, and a cos that is off by a fraction of an ulp in
-//     ONE direction for many frames is a gain error.
+//   * frame offsets are cut into absolute windows of 32 frames [32k, 32k + 32).  The window's centre frame gets the
+//     binary64 evaluation (s2_math.h) of 2^x and of sin / cos of its angle, kept as hi + lo binary32 pairs;
+//   * 2^x of a frame, x = RN(m * amount) exactly as the reference rounds it: 2^xc * 2^(x - xc), the second factor a
+//     degree-4 polynomial in binary32 (|x - xc| <= 2^-5): correctly rounded but for ~0.1 % of arguments;
+//   * fl = RN(2^x * cutoff) and theta = RN(RN(2 pi fl) / sr): the reference's own operations; the division by the
+//     launch constant sr as q = a * (1/sr) plus one residual step (Markstein): the IEEE quotient for every a at the
+//     usual rates (tools/check_cutoff.cpp checks 8 / 16 / 22.05 / 32 / 44.1 / 48 / 88.2 / 96 / 192 kHz exhaustively),
+//     within an ulp for any other rate;
+//   * sin / cos of a frame: the angle-addition correction in binary32 around the centre,
+//     sin(tc + d) = S + (C sin d - S (1 - cos d)), |d| <= 2^-7 so sin d = d - d^3/6 and 1 - cos d = d^2/2 to 2e-10:
+//     <= 1e-9 beyond a correct rounding (the rounded-once value in 99.5 % of the frames; glibc's own sinf / cosf,
+//     which the oracle calls, differ from it in 1.3 %);
 //   * the second-order coefficients from (sin, cos): the reference's own binary32 operations, one rounding each;
-//     its num / den as reciprocal estimate, quotient, one residual correction (correctly rounded but for ~1e-6
-//     of operands, where it is the neighbouring value), so the scalar and the packed (two frames per
-//     instruction) forms are the same operations and give the same bits.
+//     its num / den as reciprocal estimate, quotient, one residual correction (the IEEE quotient but for 1e-7 of
+//     operands), so the scalar and the packed (two frames per instruction) forms are the same operations and give
+//     the same bits.
 //   * one-pole k = e^-theta: binary32 throughout (2^x by ex2.approx, the product theta * log2 e in two parts).
 //     k only sets the cutoff — the filter's DC gain is (1-k)/(1-k) — so 2-3 ulp of k are far below the bar.
 //
 // PURITY.  Which evaluation a frame gets depends only on the voice's parameters and the frame's absolute offset
 // (window index, envelope segment), never on how a render was cut into calls or chunks: a window is "valid" iff
-// it lies inside one envelope segment and its centre angle times the segment's sweep rate stays below 2^-7;
-// frames of other windows get the full evaluation.  Every path of the kernels (moving-cutoff chunks packed and
-// scalar, the general per-frame path, the time-split kernels) calls the functions below, so
-// test_split_invariance_bitwise and test_paths_agree_bitwise keep holding.
+// it lies inside one envelope segment, its centre angle times the segment's sweep rate stays below 2^-7 and the
+// exponent moves by less than 2^-5 across half of it; frames of other windows get the full evaluation.  Every path of
+// the kernels (moving-cutoff chunks packed and scalar, the general per-frame path, the time-split kernels) calls the
+// functions below, so test_split_invariance_bitwise and test_paths_agree_bitwise keep holding.
 //
 // Host-and-device: tools/check_cutoff.cpp runs the scalar forms on the CPU.
 #pragma once
@@ -128,22 +133,22 @@ template <class T> S2C_FN T vaddp(T prod, T y, float one) { return vfma(prod, sp
 
 constexpr float kTwoPi = 6.28318548202636718750f;      // 2.0 * std::f32::consts::PI in binary32 (filters.rs:21)
 constexpr float kWinDelta = 0.0078125f;                // 2^-7: the largest |theta - theta_c| a valid window allows
+constexpr float kWinDeltaX = 0.03125f;                 // 2^-5: the largest |x - x_c| (exponent of 2^x)
 constexpr uint32_t kWinShift = 5;                      // windows of 32 frames
 constexpr float kThetaMax = 3.125f;                    // a valid window's centre angle: theta stays below pi
 
-// theta = 2^(m * amount) * theta0, theta0 = (2 pi cutoff) / sr (dsp_filters.rs:107 / filters.rs:21 with the sign
-// dropped; process.rs:231-250), 2^x by the hardware
+// theta = (2 pi fl) / sr (dsp_filters.rs:107, filters.rs:21 with the sign dropped).  rsr = RN(1 / sr).
 template <class T>
-S2C_FN T sweep_at(T m, float amount) { return vex2(vmul(m, splat<T>(amount))); }
-template <class T>
-S2C_FN T theta_at(T m, float amount, float theta0) { return vmul(sweep_at<T>(m, amount), splat<T>(theta0)); }
-// theta - thc for a frame inside the window centred on thc: ONE fma of the sweep factor (exact product, one
-// rounding).  Written as an fma on purpose: ptxas contracts a packed multiply feeding a packed add anyway, and the
-// scalar and packed forms must be the same operations.
-template <class T>
-S2C_FN T delta_at(T m, float amount, float theta0, float thc) {
-    return vfma(sweep_at<T>(m, amount), splat<T>(theta0), splat<T>(-thc));
+S2C_FN T theta_of(T fl, float sr, float rsr) {
+    const T a = vmul(fl, splat<T>(kTwoPi));
+    const T q = vmul(a, splat<T>(rsr));
+    const T e = vfma(splat<T>(-sr), q, a);             // exact residual a - sr q
+    return vfma(e, splat<T>(rsr), q);
 }
+
+// theta of the one-pole's moving cutoff: 2^(m * amount) * theta0, theta0 = (2 pi cutoff) / sr, 2^x by the hardware
+template <class T>
+S2C_FN T theta_at(T m, float amount, float theta0) { return vmul(vex2(vmul(m, splat<T>(amount))), splat<T>(theta0)); }
 
 // num / den for den in [1, 9], |num| <= 8: reciprocal estimate, quotient, one residual correction.  nden = -den.
 template <class T>
@@ -166,29 +171,17 @@ S2C_FN T exp_neg_fast(T th) {
     return vfma(e, vmul(tl, splat<T>(-0x1.62e430p-1f)), e);
 }
 
-// The centre of one 32-frame window of a cutoff trajectory: theta_c and the binary64 values of the functions the
-// filter needs there, as hi + lo binary32 pairs.  valid = 0: frames of this window take the full evaluation.
+// The centre of one 32-frame window of a cutoff trajectory: the exponent and the angle of its centre frame and the
+// binary64 values of 2^x, sin and cos there, as hi + lo binary32 pairs.  valid = 0: frames of this window take the
+// full evaluation.
 struct Window {
     uint32_t k;             // window index (frame offset >> 5); 0xffffffff = none yet
-    uint32_t valid;         // 0: frames of this window take the full evaluation; 1: window evaluation per frame;
-                            // 2: window evaluation at every 4th frame, linear in between (see kInterpRate)
-    float thc;              // theta of the centre frame
-    float Ah, Al, Bh, Bl;   // sin (A) and cos (B) of thc as hi + lo
-    // scalar form only: the interpolation interval [knode, knode + 4) last evaluated
-    uint32_t knode;
-    float qa, coa, dq, dco;
+    uint32_t valid;
+    float xc;               // RN(m * amount) of the centre frame
+    float Eh, El;           // 2^xc
+    float thc;              // theta of the centre frame, through the reference's chain from RN(2^xc)
+    float Ah, Al, Bh, Bl;   // sin (A) and cos (B) of thc
 };
-
-// Interpolation (second-order filters).  q = (1 - h) / (1 + h), h = damping/2 * sin(theta), and cos(theta) are smooth
-// in the frame offset; the algebra that turns them into (alpha, beta, gamma) is where the reference's rounding lives
-// (alpha = (1/2 + beta - gamma) / 4 cancels).  So q and cos are evaluated through the window at the frames of an
-// absolute grid of 4 and taken linear in between, and the coefficient algebra runs per frame on them exactly as the
-// reference's does.  Linear interpolation of cos over an interval of d radians is off by at most d^2 / 8; with the
-// angle moving by the factor 2^(amt * es) per frame, d = 4 ln2 |amt es| theta, which makes the relative error of
-// alpha (~theta^2 / 4 at low cutoffs, the sensitive end) (4 ln2 |amt es|)^2 / 2: 9e-8 for the bench bank's sweep
-// (1.5 octaves in 200 ms), 4.2e-6 for the default patch's (10 octaves in 200 ms) — against the 2e-4 by which the
-// reference's own binary32 alpha scatters from frame to frame at 100 Hz.  Faster sweeps evaluate every frame.
-constexpr float kInterpRate12 = 0.0135f;      // 12 |amt es| <= this
 
 S2C_FN void split_hi_lo(double v, float* hi, float* lo) {
     *hi = (float)v;
@@ -205,6 +198,20 @@ S2C_FN void window_sincos(const Window& W, T d, T* s, T* c) {
     *s = vadd(splat<T>(W.Ah), vadd(splat<T>(W.Al), cs));
     const T cc = vfma(splat<T>(-W.Bh), w, vmul(splat<T>(-W.Ah), sd));     // -(S sin d + C (1 - cos d))
     *c = vadd(splat<T>(W.Bh), vadd(splat<T>(W.Bl), cc));
+}
+
+// 2^x for x = RN(m * amount) inside the window (|x - xc| <= 2^-5): 2^xc * 2^d, 2^d - 1 = t (1 + t/2 (1 + t/3 (1 + t/4))),
+// t = d ln 2.  x is a rounded product and must stay one: the difference is taken through an fma by an opaque 1
+// (see the hazard note), in the scalar form too, so both are the same operations.
+template <class T>
+S2C_FN T sweep_exact(const Window& W, T x, float one) {
+    const T d = vfma(x, splat<T>(one), splat<T>(-W.xc));                  // exact (Sterbenz) or far below an ulp of x
+    const T t = vmul(d, splat<T>(0x1.62e430p-1f));
+    T p = vfma(t, splat<T>(0x1.555556p-5f), splat<T>(0x1.555556p-3f));    // t/24 + 1/6
+    p = vfma(p, t, splat<T>(0.5f));
+    p = vfma(p, t, splat<T>(1.0f));
+    const T em = vmul(t, p);                                              // 2^d - 1
+    return vadd(splat<T>(W.Eh), vfma(splat<T>(W.Eh), em, splat<T>(W.El)));
 }
 
 // q = (1 - h) / (1 + h), h = hd * sin (dsp_filters.rs:108 / :158 with beta = q / 2), for 1 <= 1 + h <= 9
@@ -236,14 +243,6 @@ S2C_FN void biquad_from_q_cos(T q, T co, float one, T* c0, T* c1, T* c2) {
 template <bool HIGH_PASS, class T>
 S2C_FN void biquad_lp_hp(T s, T co, float hd, float one, T* c0, T* c1, T* c2) {
     biquad_from_q_cos<HIGH_PASS, T>(quotient_of<T>(s, hd, one), co, one, c0, c1, c2);
-}
-
-// (q, cos) of the frame(s) whose mod-envelope value is m, through window W
-template <class T>
-S2C_FN void node_q_cos(const Window& W, T m, float amount, float theta0, float hd, float one, T* q, T* co) {
-    T s;
-    window_sincos<T>(W, delta_at<T>(m, amount, theta0, W.thc), &s, co);
-    *q = quotient_of<T>(s, hd, one);
 }
 
 // The same coefficients for any operands (frames outside valid windows): inside the straight-line division's

@@ -260,57 +260,87 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
 // MOVING cutoff (s2_cutoff.h): the mod envelope is in a ramp (attack / decay / release) and the cutoff follows it.
 
 struct CutP {            // per-voice constants of the moving evaluation
-    float theta0;        // (2 pi cutoff) / sr
+    float lpf;           // the patch's cutoff in Hz
+    float theta0;        // (2 pi cutoff) / sr — the one-pole's form
     float amt;           // mod_env_to_lpf_freq
     float damp, hd;      // damping, damping / 2
+    float sr, rsr;       // sample rate and RN(1 / sr)
 };
-__device__ __forceinline__ CutP make_cutp(float lpf, float amt_lpf, float damp, float sr) {
+__device__ __forceinline__ CutP cutp_of(float lpf, float theta0, float amt_lpf, float damp, float sr, float rsr) {
     CutP c;
-    c.theta0 = theta_ref(lpf, sr);
+    c.lpf = lpf;
+    c.theta0 = theta0;
     c.amt = amt_lpf;
     c.damp = damp;
     c.hd = __fmul_rn(damp, 0.5f);
+    c.sr = sr;
+    c.rsr = rsr;
     return c;
+}
+__device__ __forceinline__ CutP make_cutp(float lpf, float amt_lpf, float damp, float sr) {
+    return cutp_of(lpf, theta_ref(lpf, sr), amt_lpf, damp, sr, __frcp_rn(sr));
+}
+
+// theta of the frame whose mod envelope is m by the reference's own chain, 2^x in binary64 rounded once
+// (process.rs:244-246, dsp_filters.rs:107): the evaluation of frames outside valid windows and of window centres.
+__device__ __forceinline__ float theta_full(const CutP& cp, float m) {
+    return theta_ref(__fmul_rn(s2_exp2f(__fmul_rn(m, cp.amt)), cp.lpf), cp.sr);
 }
 
 // The window of frame offset n inside mod-envelope segment sm (a ramp).  Valid iff the 32 frames of the window
-// lie in the segment, the centre angle leaves room below pi, the sweep across half a window stays within
-// 2^-7 (theta changes by the factor 2^(amt * es) per frame: |d| <= thc * 16 ln 2 |amt es| (1 + ...) < thc * 12 |amt es|)
+// lie in the segment, the centre angle leaves room below pi, across half a window the exponent stays within 2^-5
+// (it moves by amt * es per frame) and the angle within 2^-7 (|d| <= thc * 16 ln 2 |amt es| (1 + ...) < thc * 12 |amt es|)
 // and the damping suits the straight-line division.  A pure function of (voice, n >> 5).
 template <int FILTER>
 __device__ __forceinline__ void make_window_inl(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
     const uint32_t k = n >> s2c::kWinShift;
     W.k = k;
     const uint32_t w0 = k << s2c::kWinShift;
-    const float xc = __uint2float_rn(w0 + 16u);
-    const float thc = s2c::theta_at<float>(seg_eval(sm, xc), cp.amt, cp.theta0);
-    const float r12 = __fmul_rn(fabsf(__fmul_rn(cp.amt, sm.es)), 12.0f);
-    bool valid = w0 >= sm.nbeg && w0 + 32u <= sm.nend && thc <= s2c::kThetaMax && r12 < 0.5f &&
+    const float xc = __fmul_rn(seg_eval(sm, __uint2float_rn(w0 + 16u)), cp.amt);
+    const float r = fabsf(__fmul_rn(cp.amt, sm.es));
+    const float r12 = __fmul_rn(r, 12.0f);
+    const bool in_range = xc > -100.0f && xc < 100.0f && __fmul_rn(r, 17.0f) <= s2c::kWinDeltaX;
+    double Ed = 0.0;
+    float thc = 4.0f;
+    if (in_range) {
+        Ed = s2_exp2_d(xc);
+        thc = theta_ref(__fmul_rn((float)Ed, cp.lpf), cp.sr);
+    }
+    bool valid = in_range && w0 >= sm.nbeg && w0 + 32u <= sm.nend && thc <= s2c::kThetaMax &&
                  __fmul_rn(thc, r12) <= s2c::kWinDelta;
     if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) valid = valid && cp.hd >= 0.0f && cp.hd <= 8.0f;
     if (FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_BP) valid = false;      // these never look at a window
-    W.valid = !valid ? 0u : ((FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) && r12 <= s2c::kInterpRate12) ? 2u : 1u;
+    W.valid = valid ? 1u : 0u;
+    W.xc = xc;
     W.thc = thc;
-    W.knode = 0xffffffffu;
-    W.qa = W.coa = W.dq = W.dco = 0.0f;
     if (valid) {
         double sd, cd;
         s2_sincos_d((double)thc, &sd, &cd);
+        s2c::split_hi_lo(Ed, &W.Eh, &W.El);
         s2c::split_hi_lo(sd, &W.Ah, &W.Al);
         s2c::split_hi_lo(cd, &W.Bh, &W.Bl);
     } else {
-        W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+        W.Eh = W.El = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
     }
 }
 
 __device__ __forceinline__ void window_none(s2c::Window& W) {
-    W.k = 0xffffffffu; W.valid = 0u; W.thc = 0.0f; W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
-    W.knode = 0xffffffffu; W.qa = W.coa = W.dq = W.dco = 0.0f;
+    W.k = 0xffffffffu; W.valid = 0u; W.xc = 0.0f; W.thc = 0.0f;
+    W.Eh = W.El = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
 }
 
 template <int FILTER>
 __device__ __noinline__ void make_window(s2c::Window& W, const SegEnv& sm, const CutP& cp, uint32_t n) {
     make_window_inl<FILTER>(W, sm, cp, n);
+}
+
+// sin and cos of the angle of the frame(s) whose mod envelope is m, inside valid window W: the reference's chain
+// in binary32 around the window's centre (s2_cutoff.h).  T = float or float2, the same operations.
+template <class T>
+__device__ __forceinline__ void window_frame_sincos(const s2c::Window& W, const CutP& cp, float one, T m, T* s, T* co) {
+    const T E = s2c::sweep_exact<T>(W, s2c::vmul(m, s2c::splat<T>(cp.amt)), one);
+    const T th = s2c::theta_of<T>(s2c::vmul(E, s2c::splat<T>(cp.lpf)), cp.sr, cp.rsr);
+    s2c::window_sincos<T>(W, s2c::vadd(th, s2c::splat<T>(-W.thc)), s, co);
 }
 
 // Coefficients of one moving frame (scalar form): m = the mod envelope at frame n (inside segment sm).
@@ -325,25 +355,11 @@ __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const Seg
         c.c2 = 0.0f;
         return;
     }
-    if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp); return; }
+    if (FILTER == FILT_BIQUAD_BP) { make_filt_theta<FILTER>(c, theta_full(cp, m), cp.damp); return; }
     if ((n >> s2c::kWinShift) != W.k) make_window<FILTER>(W, sm, cp, n);
-    if (W.valid == 2u && (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP)) {
-        // q and cos at the frames of the absolute grid of 4 around n, linear in between (s2_cutoff.h)
-        const uint32_t k = n & ~3u;
-        if (k != W.knode) {
-            float qb, cob;
-            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k)), cp.amt, cp.theta0, cp.hd, one, &W.qa, &W.coa);
-            s2c::node_q_cos<float>(W, seg_eval(sm, __uint2float_rn(k + 4u)), cp.amt, cp.theta0, cp.hd, one, &qb, &cob);
-            W.dq = __fmul_rn(__fsub_rn(qb, W.qa), 0.25f);
-            W.dco = __fmul_rn(__fsub_rn(cob, W.coa), 0.25f);
-            W.knode = k;
-        }
-        const float j = __uint2float_rn(n & 3u);
-        s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float>(__fmaf_rn(j, W.dq, W.qa), __fmaf_rn(j, W.dco, W.coa), one,
-                                                                &c.c0, &c.c1, &c.c2);
-    } else if (W.valid) {
+    if (W.valid) {
         float s, co;
-        s2c::window_sincos<float>(W, s2c::delta_at<float>(m, cp.amt, cp.theta0, W.thc), &s, &co);
+        window_frame_sincos<float>(W, cp, one, m, &s, &co);
         if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
             s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
         } else {
@@ -354,10 +370,10 @@ __device__ __forceinline__ void moving_coefs(FiltC& c, s2c::Window& W, const Seg
         }
     } else if (FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP) {
         float s, co;
-        s2_sincosf(s2c::theta_at<float>(m, cp.amt, cp.theta0), &s, &co);
+        s2_sincosf(theta_full(cp, m), &s, &co);
         s2c::biquad_lp_hp_any<FILTER == FILT_BIQUAD_HP>(s, co, cp.hd, one, &c.c0, &c.c1, &c.c2);
     } else {
-        make_filt_theta<FILTER>(c, s2c::theta_at<float>(m, cp.amt, cp.theta0), cp.damp);
+        make_filt_theta<FILTER>(c, theta_full(cp, m), cp.damp);
     }
 }
 
@@ -691,18 +707,16 @@ struct MovV {
     CutP cp;
     float mes, mnex0, mey0;      // the mod envelope's segment line (the whole chunk lies inside it)
     bool moving;                 // false: this lane's cutoff rests (F.c0 .. F.c2) while others of the warp move
-    float q_rest, co_rest;       // a resting lane's 2 beta and cos(theta): interpolation nodes that never move
 };
 
 // Moving-cutoff chunk, packed: the period is constant but the mod envelope is in a ramp, so the cutoff — and with
 // it the filter coefficients — changes every frame (process.rs:148-152, 363-371; the first 200 ms of every note of
 // the default patch, synth.rs:141-150).  Preconditions (the classifier checks them for every lane): the chunk lies
 // inside the lane's current amp-envelope segment (F.es .., as G_LINE); for every MOVING lane it starts at a multiple
-// of 32 frames, lies inside one segment of the mod envelope, and (second-order filters) its window W is valid at
-// level 2: q and cos at every 4th frame, linear in between, the coefficient algebra per frame (s2_cutoff.h).  The
-// one-pole evaluates k = e^-theta every frame.  Lanes whose cutoff rests run the same code: their interpolation
-// nodes are their own 2 beta and cos(theta), which the algebra turns into their resting coefficients bit for bit
-// (one-pole: they select their constants).
+// of 32 frames, lies inside one segment of the mod envelope, and (second-order filters) its window W is valid.
+// Every frame's coefficients come from the reference's own chain, two frames per instruction (s2_cutoff.h): 2^x
+// around the window's centre, the angle, sin / cos by angle addition, the coefficient algebra.  The one-pole
+// evaluates k = e^-theta every frame.  Lanes whose cutoff rests run the same code and select their constants.
 // ONE variant per oscillator kind and 4 frames per trip, on purpose: a moving-cutoff step walks through the
 // classifier, the window's binary64 code, this loop and the write-back once per chunk, and with 8-frame trips in
 // four variants that path outgrew the 32 KB instruction cache of an SM — 41 % of the stall samples of such a launch
@@ -712,50 +726,29 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
                                                 float one, uint32_t kind, uint32_t rot, uint32_t n0,
                                                 float* __restrict__ row, const float* sintab) {
     static_assert(FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
-    constexpr bool INTERP = FILTER != FILT_ONE_POLE;
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
     uint32_t n = n0;
     float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     float ph = F.ph;
-    auto mod2 = [&](float2 x2) {      // the mod envelope's line at two frame offsets
-        return s2c::vaddp(pmul2(splat2(mv.mes), padd2(x2, splat2(mv.mnex0))), splat2(mv.mey0), one);
-    };
-    // nodes of the interpolation: (q, cos) at frames (x, x + 4)
-    auto nodes = [&](float x, float2* q, float2* co) {
-        s2c::node_q_cos<float2>(W, mod2(make_float2(x, __fadd_rn(x, 4.0f))), mv.cp.amt, mv.cp.theta0, mv.cp.hd, one, q, co);
-        if (!mv.moving) { *q = splat2(mv.q_rest); *co = splat2(mv.co_rest); }
-    };
-    float2 qP = splat2(0.0f), coP = splat2(0.0f);
-    float q0 = 0.0f, co0 = 0.0f;
-    if (INTERP) {
-        nodes(xf2.x, &qP, &coP);       // frames n0 and n0 + 4
-        q0 = qP.x; co0 = coP.x;
-    }
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
-        float dq = 0.0f, dco = 0.0f;
-        if (INTERP) {
-            // frames [4j, 4j + 4): from node 4j (q0, co0) to node 4j + 4 — the second of the pair evaluated one trip
-            // ago on even trips, the first of the pair evaluated now (frames 4j + 4, 4j + 8) on odd ones
-            if (j & 1) nodes(__fadd_rn(xf2.x, 4.0f), &qP, &coP);
-            const float q1 = (j & 1) ? qP.x : qP.y, co1 = (j & 1) ? coP.x : coP.y;
-            dq = __fmul_rn(__fsub_rn(q1, q0), 0.25f);
-            dco = __fmul_rn(__fsub_rn(co1, co0), 0.25f);
-        }
         float o4[4];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            // the mod envelope's line at the two frame offsets
+            const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
             float2 c0, c1, c2;
-            if (INTERP) {
-                const float2 j2 = make_float2(2.0f * h, 2.0f * h + 1.0f);
-                s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(pfma2(j2, splat2(dq), splat2(q0)), pfma2(j2, splat2(dco), splat2(co0)),
-                                                                         one, &c0, &c1, &c2);
-            } else {
-                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(mod2(xf2), mv.cp.amt, mv.cp.theta0));
+            if (FILTER == FILT_ONE_POLE) {
+                c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
                 c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
                 c2 = splat2(0.0f);
                 if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); }
+            } else {
+                float2 s2, co2;
+                window_frame_sincos<float2>(W, mv.cp, one, m2, &s2, &co2);
+                s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2, co2, mv.cp.hd, one, &c0, &c1, &c2);
+                if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); c2 = splat2(F.c2); }
             }
             FiltC ca, cb;
             ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
@@ -776,10 +769,6 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
             xf2 = padd2(xf2, splat2(2.0f));
         }
         *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        if (INTERP) {
-            q0 = (j & 1) ? qP.x : qP.y;
-            co0 = (j & 1) ? coP.x : coP.y;
-        }
     }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;

@@ -85,6 +85,7 @@ render_kernel(const RenderArgs a) {
     if (vbase >= a.slot_end) return;
     const uint32_t vp = a.vpad;
     const float sr = a.sample_rate;
+    const float rsr = __frcp_rn(sr);
     const float one = a.one;
     Cold& C = *reinterpret_cast<Cold*>(cold_base + lane * kColdWords);
     float* row = tile + lane * kTileStride;
@@ -346,8 +347,8 @@ render_kernel(const RenderArgs a) {
                         // a stage boundary inside the chunk: the compact per-frame loop on the resting constants
                         MovV mv;
                         mv.moving = false;
-                        mv.cp.theta0 = 0.0f; mv.cp.amt = 0.0f; mv.cp.damp = 0.0f; mv.cp.hd = 0.0f;
-                        mv.mes = mv.mnex0 = mv.mey0 = 0.0f; mv.q_rest = mv.co_rest = 0.0f;
+                        mv.cp = cutp_of(0.0f, 0.0f, 0.0f, 0.0f, sr, rsr);
+                        mv.mes = mv.mnex0 = mv.mey0 = 0.0f;
                         const SegEnv none = {0.0f, 0.0f, 0.0f, 1u, 0u, 4};
                         chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.amp, mv, none, one, kind, rot, n, row + hh, sintab, nullptr);
                     } else {
@@ -381,17 +382,15 @@ render_kernel(const RenderArgs a) {
                 // Moving-cutoff chunk.  Lanes whose cutoff rests (flag 4 clear) run the same code on their constants.
                 MovV mv;
                 mv.moving = active && (C.flags & 4u) != 0u;
-                mv.cp.theta0 = C.theta0; mv.cp.amt = C.amt_lpf; mv.cp.damp = C.damp; mv.cp.hd = __fmul_rn(C.damp, 0.5f);
+                mv.cp = cutp_of(C.lpf, C.theta0, C.amt_lpf, C.damp, sr, rsr);
                 SegEnv sm = C.msg;
                 mv.mes = sm.es; mv.mnex0 = sm.nex0; mv.mey0 = sm.ey0;
-                mv.q_rest = C.fc.c1; mv.co_rest = C.fc.co;
                 constexpr bool kPackable = FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP;
                 if (filt_uniform) {
                     // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once
                     const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + leader * kColdWords);
                     const uint32_t n_lead = __shfl_sync(0xffffffffu, n, leader);   // inactive lanes hold other offsets
-                    CutP cpl;
-                    cpl.theta0 = CL.theta0; cpl.amt = CL.amt_lpf; cpl.damp = CL.damp; cpl.hd = __fmul_rn(CL.damp, 0.5f);
+                    const CutP cpl = cutp_of(CL.lpf, CL.theta0, CL.amt_lpf, CL.damp, sr, rsr);
                     const SegEnv sml = CL.msg;
                     modcut_coefficients<FILTER>(sml, cpl, one, n_lead, lane, ctab);
                     __syncwarp();
@@ -404,7 +403,7 @@ render_kernel(const RenderArgs a) {
                     __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
                 } else {
                     // packed: every lane inside one amp segment; moving ones aligned and (second-order filters) with a
-                    // window at level 2.  Otherwise one frame at a time.
+                    // valid window.  Otherwise one frame at a time.
                     bool packed = false;
                     s2c::Window W;
                     window_none(W);
@@ -420,7 +419,7 @@ render_kernel(const RenderArgs a) {
                             ok = (n & 31u) == 0u;
                             if (FILTER != FILT_ONE_POLE && ok) {
                                 make_window_inl<FILTER>(W, sm, mv.cp, n);
-                                ok = W.valid == 2u;
+                                ok = W.valid != 0u;
                             }
                         }
                         packed = a.force_path == 0u && __all_sync(0xffffffffu, ok);

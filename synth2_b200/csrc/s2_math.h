@@ -99,6 +99,14 @@ S2_HD float s2_exp2f(float x) {
     return (float)s2_scale2(r, k);                        // one rounding (subnormal results round here too)
 }
 
+// 2^x in binary64 for a binary32 x in (-150, 128] (the centre of a moving-cutoff window, s2_cutoff.h)
+S2_HD double s2_exp2_d(float x) {
+    const double xd = (double)x;
+    int k;
+    const double kd = s2_rint_int(xd, &k);
+    return s2_scale2(s2_exp_kernel((xd - kd) * S2K(S2K_LN2)), k);
+}
+
 // e^x, x binary32.  Cody-Waite reduction x = k*ln2 + r, |r| <= 0.35.
 S2_HD float s2_expf(float x) {
     if (!(x > -104.0f)) return x != x ? x : 0.0f;

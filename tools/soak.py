@@ -15,7 +15,7 @@ count = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 worst = 0.0
 for seed in range(first, first + count):
     T.test_random_banks_against_oracle(seed)
-print(f"default / NV2 / PC / pipelined paths: seeds {first}..{first + count - 1} within tolerance", flush=True)
+print(f"default / one-frame-at-a-time moving cutoff / general / pipelined paths: seeds {first}..{first + count - 1} within tolerance", flush=True)
 
 for seed in range(first, first + count // 2):
     rng = np.random.default_rng(7000 + seed)
