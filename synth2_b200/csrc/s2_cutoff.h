@@ -178,7 +178,7 @@ struct Window {
     uint32_t k;             // window index (frame offset >> 5); 0xffffffff = none yet
     uint32_t valid;
     float xc;               // RN(m * amount) of the centre frame
-    float Eh, El;           // 2^xc
+    float Eh, Er;           // 2^xc = Eh (1 + Er)
     float thc;              // theta of the centre frame, through the reference's chain from RN(2^xc)
     float Ah, Al, Bh, Bl;   // sin (A) and cos (B) of thc
 };
@@ -187,31 +187,38 @@ S2C_FN void split_hi_lo(double v, float* hi, float* lo) {
     *hi = (float)v;
     *lo = (float)(v - (double)*hi);
 }
+// v = hi (1 + rel), |rel| <= 2^-24 known to ~2^-24 of itself
+S2C_FN void split_hi_rel(double v, float* hi, float* rel) {
+    float lo;
+    split_hi_lo(v, hi, &lo);
+    *rel = S2C_DIV(lo, *hi);
+}
 
-// sin(thc + d), cos(thc + d) from the window (|d| <= 2^-7)
+// sin(thc + d), cos(thc + d) from the window (|d| <= 2^-7):
+// S + (C sin d - S (1 - cos d)) and C - (S sin d + C (1 - cos d)), the low parts of S and C folded into the
+// second-order terms.
 template <class T>
 S2C_FN void window_sincos(const Window& W, T d, T* s, T* c) {
     const T z = vmul(d, d);
     const T sd = vfma(vmul(d, z), splat<T>(-0x1.555556p-3f), d);          // sin d = d - d^3 / 6
-    const T w = vmul(z, splat<T>(0.5f));                                  // 1 - cos d = d^2 / 2
-    const T cs = vfma(splat<T>(W.Bh), sd, vmul(splat<T>(-W.Ah), w));      // C sin d - S (1 - cos d)
-    *s = vadd(splat<T>(W.Ah), vadd(splat<T>(W.Al), cs));
-    const T cc = vfma(splat<T>(-W.Bh), w, vmul(splat<T>(-W.Ah), sd));     // -(S sin d + C (1 - cos d))
-    *c = vadd(splat<T>(W.Bh), vadd(splat<T>(W.Bl), cc));
+    const T ws = vfma(splat<T>(-0.5f * W.Ah), z, splat<T>(W.Al));         // Al - S d^2 / 2
+    *s = vadd(splat<T>(W.Ah), vfma(splat<T>(W.Bh), sd, ws));
+    const T wc = vfma(splat<T>(-0.5f * W.Bh), z, splat<T>(W.Bl));         // Bl - C d^2 / 2
+    *c = vadd(splat<T>(W.Bh), vfma(splat<T>(-W.Ah), sd, wc));
 }
 
-// 2^x for x = RN(m * amount) inside the window (|x - xc| <= 2^-5): 2^xc * 2^d, 2^d - 1 = t (1 + t/2 (1 + t/3 (1 + t/4))),
-// t = d ln 2.  x is a rounded product and must stay one: the difference is taken through an fma by an opaque 1
-// (see the hazard note), in the scalar form too, so both are the same operations.
+// 2^x for x = RN(m * amount) inside the window (|x - xc| <= 2^-5): 2^xc * 2^d = Eh (1 + Er + (2^d - 1)),
+// 2^d - 1 = d (L + d (L^2/2 + d (L^3/6 + d L^4/24))), L = ln 2.  x is a rounded product and must stay one: the
+// difference is taken through an fma by an opaque 1 (see the hazard note), in the scalar form too, so both are the
+// same operations.
 template <class T>
 S2C_FN T sweep_exact(const Window& W, T x, float one) {
     const T d = vfma(x, splat<T>(one), splat<T>(-W.xc));                  // exact (Sterbenz) or far below an ulp of x
-    const T t = vmul(d, splat<T>(0x1.62e430p-1f));
-    T p = vfma(t, splat<T>(0x1.555556p-5f), splat<T>(0x1.555556p-3f));    // t/24 + 1/6
-    p = vfma(p, t, splat<T>(0.5f));
-    p = vfma(p, t, splat<T>(1.0f));
-    const T em = vmul(t, p);                                              // 2^d - 1
-    return vadd(splat<T>(W.Eh), vfma(splat<T>(W.Eh), em, splat<T>(W.El)));
+    T p = vfma(d, splat<T>(0x1.3b2ab6p-7f), splat<T>(0x1.c6b08ep-5f));    // L^4/24 d + L^3/6
+    p = vfma(p, d, splat<T>(0x1.ebfbe0p-3f));                             // + L^2/2
+    p = vfma(p, d, splat<T>(0x1.62e430p-1f));                             // + L
+    const T em = vfma(d, p, splat<T>(W.Er));
+    return vfma(splat<T>(W.Eh), em, splat<T>(W.Eh));
 }
 
 // q = (1 - h) / (1 + h), h = hd * sin (dsp_filters.rs:108 / :158 with beta = q / 2), for 1 <= 1 + h <= 9

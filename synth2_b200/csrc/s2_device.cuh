@@ -316,17 +316,17 @@ __device__ __forceinline__ void make_window_inl(s2c::Window& W, const SegEnv& sm
     if (valid) {
         double sd, cd;
         s2_sincos_d((double)thc, &sd, &cd);
-        s2c::split_hi_lo(Ed, &W.Eh, &W.El);
+        s2c::split_hi_rel(Ed, &W.Eh, &W.Er);
         s2c::split_hi_lo(sd, &W.Ah, &W.Al);
         s2c::split_hi_lo(cd, &W.Bh, &W.Bl);
     } else {
-        W.Eh = W.El = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+        W.Eh = W.Er = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
     }
 }
 
 __device__ __forceinline__ void window_none(s2c::Window& W) {
     W.k = 0xffffffffu; W.valid = 0u; W.xc = 0.0f; W.thc = 0.0f;
-    W.Eh = W.El = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
+    W.Eh = W.Er = W.Ah = W.Al = W.Bh = W.Bl = 0.0f;
 }
 
 template <int FILTER>
@@ -734,11 +734,17 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
         float o4[4];
+#ifdef S2_EXP_HALFCOEF
+        float2 kc0 = splat2(0.0f), kc1 = kc0, kc2 = kc0;
+#endif
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             // the mod envelope's line at the two frame offsets
             const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
             float2 c0, c1, c2;
+#ifdef S2_EXP_HALFCOEF
+            if (h == 1) { c0 = kc0; c1 = kc1; c2 = kc2; } else
+#endif
             if (FILTER == FILT_ONE_POLE) {
                 c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
                 c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
@@ -750,6 +756,9 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
                 s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2, co2, mv.cp.hd, one, &c0, &c1, &c2);
                 if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); c2 = splat2(F.c2); }
             }
+#ifdef S2_EXP_HALFCOEF
+            kc0 = c0; kc1 = c1; kc2 = c2;
+#endif
             FiltC ca, cb;
             ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
             cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
@@ -812,6 +821,22 @@ __device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvQ* __restrict
     }
     F.ph = ph;
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+}
+
+// The amp envelope of a lane whose segment ends inside a chunk that ran with a gain of exactly 1 (the packed loops
+// take the envelope as one line): out = RN(y * g), as every other path rounds it.
+static __device__ __noinline__ void edge_gain(const EnvQ* __restrict__ amp, float* __restrict__ row, uint32_t n0) {
+    SegEnv sa = seg_env(*amp, n0);
+    uint32_t n = n0;
+    float xf = __uint2float_rn(n0);
+#pragma unroll 1
+    for (int i = 0; i < kChunk; i++) {
+        float g;
+        if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(*amp, xf); sa = seg_env(*amp, n + 1u); }
+        row[i] = __fmul_rn(row[i], g);
+        n += 1u;
+        xf = __fadd_rn(xf, 1.0f);
+    }
 }
 
 // One frame per lane: the filter coefficients of frames n0 .. n0 + 31 of a cutoff trajectory shared by the warp.

@@ -334,32 +334,35 @@ render_kernel(const RenderArgs a) {
                     seg_left = __reduce_min_sync(0xffffffffu, active ? F.seg_end - n : 0xffffffffu);
                     all_gconst = __all_sync(0xffffffffu, lane_gconst);
                 }
-                const int gmode = seg_left >= (uint32_t)kChunk ? (all_gconst ? G_CONST : G_LINE) : G_ANY;
+                // A stage boundary of some lane's amp envelope inside the chunk (banks of the fast hash form): those
+                // lanes run the chunk with a gain of exactly 1 and multiply their 32 frames by the envelope
+                // afterwards (edge_gain) — one rounding either way.
+                bool edge = false;
+                int gmode = all_gconst ? G_CONST : G_LINE;
+                if (seg_left < (uint32_t)kChunk) {
+                    gmode = G_ANY;
+                    if (fasthash) {
+                        gmode = G_LINE;
+                        edge = active && F.seg_end - n < (uint32_t)kChunk;
+                        if (edge) { F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f; }
+                    }
+                }
                 // Run: whole tiles for as long as the classification holds, each with its straight-line write-back
                 // (inactive voices run the same code on zeroed constants; their rows are cleared)
                 uint32_t reps = 0;
-                if (simple_store && gmode != G_ANY && h0 == 0u && tcnt == kTile)
+                if (simple_store && seg_left >= kTile && h0 == 0u && tcnt == kTile)
                     reps = min(min(min(fast_left, seg_left), f16 - t0) / kTile, kRunTiles);
                 const uint32_t n_chunks = reps ? reps * (kTile / (uint32_t)kChunk) : 1u;
                 uint32_t hh = h0, ts = t0;
                 for (uint32_t k = 0; k < n_chunks; k++) {
-                    if (gmode == G_ANY && fasthash) {
-                        // a stage boundary inside the chunk: the compact per-frame loop on the resting constants
-                        MovV mv;
-                        mv.moving = false;
-                        mv.cp = cutp_of(0.0f, 0.0f, 0.0f, 0.0f, sr, rsr);
-                        mv.mes = mv.mnex0 = mv.mey0 = 0.0f;
-                        const SegEnv none = {0.0f, 0.0f, 0.0f, 1u, 0u, 4};
-                        chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.amp, mv, none, one, kind, rot, n, row + hh, sintab, nullptr);
-                    } else {
-                        switch (wkind) {
-                        case 0: fast_tile<FILTER, 0, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
-                        case 1: fast_tile<FILTER, 1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
-                        case 2: fast_tile<FILTER, 2, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
-                        case 3: fast_tile<FILTER, 3, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
-                        default: fast_tile<FILTER, -1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
-                        }
+                    switch (wkind) {
+                    case 0: fast_tile<FILTER, 0, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 1: fast_tile<FILTER, 1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 2: fast_tile<FILTER, 2, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    case 3: fast_tile<FILTER, 3, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
+                    default: fast_tile<FILTER, -1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
                     }
+                    if (TRACE != TRACE_PHASE && edge) edge_gain(&C.amp, row + hh, n);
                     n += kChunk;
                     hh += (uint32_t)kChunk;
                     if (reps && hh == kTile) {
@@ -372,7 +375,7 @@ render_kernel(const RenderArgs a) {
                     }
                 }
                 fast_left -= n_chunks * (uint32_t)kChunk;
-                seg_left = gmode == G_ANY ? 0u : seg_left - n_chunks * (uint32_t)kChunk;
+                seg_left = seg_left < (uint32_t)kChunk ? 0u : seg_left - n_chunks * (uint32_t)kChunk;
                 if (reps) {
                     t0 += (reps - 1u) * kTile;               // the loop header adds the last tile
                     written = true;
@@ -402,20 +405,22 @@ render_kernel(const RenderArgs a) {
                     }
                     __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
                 } else {
-                    // packed: every lane inside one amp segment; moving ones aligned and (second-order filters) with a
-                    // valid window.  Otherwise one frame at a time.
-                    bool packed = false;
+                    // packed: the moving lanes aligned and (second-order filters) with a valid window.  Otherwise one
+                    // frame at a time.
+                    bool packed = false, edge = false;
                     s2c::Window W;
                     window_none(W);
                     if constexpr (kPackable) {
-                        // the packed form takes the amp envelope as one line through the chunk (as G_LINE)
+                        // the packed form takes the amp envelope as one line through the chunk (as G_LINE); a lane with
+                        // a stage boundary inside the chunk takes a gain of 1 and edge_gain afterwards
                         if (active && n >= F.seg_end) {
                             const SegEnv sg = seg_env(C.amp, n);
                             F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
                             lane_gconst = sg.stage == 2 || sg.stage == 4;
                         }
-                        bool ok = !active || n + kChunk <= F.seg_end;
-                        if (mv.moving && ok) {
+                        edge = active && F.seg_end - n < (uint32_t)kChunk;
+                        bool ok = true;
+                        if (mv.moving) {
                             ok = (n & 31u) == 0u;
                             if (FILTER != FILT_ONE_POLE && ok) {
                                 make_window_inl<FILTER>(W, sm, mv.cp, n);
@@ -426,11 +431,13 @@ render_kernel(const RenderArgs a) {
                     }
                     if (packed) {
                         if constexpr (kPackable) {
+                            if (edge) { F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f; }
                             switch (wkind) {
                             case 0: chunk_modcut_pk<FILTER, 0, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
                             case 1: chunk_modcut_pk<FILTER, 1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
                             default: chunk_modcut_pk<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
                             }
+                            if (TRACE != TRACE_PHASE && edge) edge_gain(&C.amp, crow, n);
                         }
                     } else {
                         chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, nullptr);

@@ -150,7 +150,7 @@ int main(int argc, char** argv) {
             const double u = (rng() >> 11) * (1.0 / 9007199254740992.0);
             Window W;
             W.xc = (float)(u * 24.0 - 12.0);
-            split_hi_lo(s2_exp2_d(W.xc), &W.Eh, &W.El);
+            split_hi_rel(s2_exp2_d(W.xc), &W.Eh, &W.Er);
             for (int j = 0; j < 16; j++) {
                 const double v = (rng() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
                 const float x = W.xc + (float)(v * kWinDeltaX);
@@ -188,7 +188,7 @@ int main(int argc, char** argv) {
                     const float xc = (float)((n & ~31u) + 16u);
                     W.xc = ((sD * (xc - A)) + 1.0f) * amt;
                     const double Ed = s2_exp2_d(W.xc);
-                    split_hi_lo(Ed, &W.Eh, &W.El);
+                    split_hi_rel(Ed, &W.Eh, &W.Er);
                     make_window(W, (((float)Ed * lpf) * kTwoPi) / sr);
                     W.k = n >> 5;
                 }
