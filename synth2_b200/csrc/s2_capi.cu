@@ -529,7 +529,7 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     b->vpad = (n_voices + 63) & ~(size_t)63;
     b->book.resize(n_voices);
     if (n_voices <= kTsMaxVoices) b->descs.assign(voices, voices + n_voices);
-    if (const char* f = getenv("S2_FORCE_PATH")) b->force_path = (f[0] == '1') ? 1u : (f[0] == '2') ? 2u : 0u;   // test hook
+    if (const char* f = getenv("S2_FORCE_PATH")) b->force_path = (f[0] >= '1' && f[0] <= '3') ? (uint32_t)(f[0] - '0') : 0u;   // test hook
 
     b->voice_of_slot.resize(n_voices);
     b->slot_of_voice.resize(n_voices);
@@ -555,6 +555,38 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
             if (a.kind != c.kind) return a.kind < c.kind;
             return a.amp_rest < c.amp_rest;
         });
+        // Instead the followers are PAIRED with voices whose cutoff rests: inside each kind, walking the sorted
+        // order, a follower and a non-follower that are next in line share an aligned lane pair (2i, 2i + 1), and the
+        // resting lane computes half of its partner's moving coefficients (chunk_modcut_pr).  Voices left without
+        // a partner come after the pairs, in the sorted order.
+        {
+            auto follows = [&](uint32_t v) { return voices[v].active && voices[v].mod_env_to_lpf_freq != 0.0f; };
+            std::vector<uint32_t> out, fq, nq;
+            out.reserve(n_voices);
+            size_t g0 = 0;
+            while (g0 < n_voices) {
+                size_t g1 = g0;
+                while (g1 < n_voices && keys[b->voice_of_slot[g1]].kind == keys[b->voice_of_slot[g0]].kind) g1++;
+                fq.clear(); nq.clear();
+                size_t fi = 0, ni = 0;             // queue heads
+                for (size_t i = g0; i < g1; i++) {
+                    const uint32_t v = b->voice_of_slot[i];
+                    (follows(v) ? fq : nq).push_back(v);
+                    if (fi < fq.size() && ni < nq.size()) {
+                        if (out.size() & 1u) { out.push_back(nq[ni++]); continue; }    // keep the pairs on even slots
+                        out.push_back(fq[fi++]);
+                        out.push_back(nq[ni++]);
+                    }
+                }
+                // the unpaired: merge the two leftovers back into the sorted order
+                std::vector<uint32_t> left(fq.begin() + fi, fq.end());
+                left.insert(left.end(), nq.begin() + ni, nq.end());
+                std::stable_sort(left.begin(), left.end(), [&](uint32_t x, uint32_t y) { return keys[x].amp_rest < keys[y].amp_rest; });
+                out.insert(out.end(), left.begin(), left.end());
+                g0 = g1;
+            }
+            b->voice_of_slot.swap(out);
+        }
         // Deal the sorted warps (32 slots each) round-robin into 8 bins laid out one after the other: every contiguous
         // eighth / quarter / half of the slot range — the voice ranges of s2_bank_set_pipeline — then holds the same
         // mix of kinds and envelope lengths, so the ranges' streams advance together.

@@ -783,6 +783,76 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
 }
 
+// The same chunk when no aligned lane pair (2i, 2i + 1) holds two moving lanes (s2_bank_create lays the slots out that
+// way where it can): the resting lane of a pair computes half of its partner's coefficients instead of idling.  Per
+// trip of 4 frames every lane evaluates ONE pair of frames of its ASSIGNED voice — its own if it moves (frames 4j,
+// 4j + 1), its partner's if it helps (frames 4j + 2, 4j + 3) — up to (q, cos), the pair swaps them by a shuffle, and
+// every lane finishes both pairs' coefficient algebra and runs its own voice.  The same functions on the same
+// operands as chunk_modcut_pk, hence the same bits; a third fewer arithmetic instructions per frame.
+template <int FILTER, int KIND, int TRACE>
+__device__ __forceinline__ void chunk_modcut_pr(FastV& F, const MovV& mv, const s2c::Window& W,
+                                                float one, uint32_t kind, uint32_t rot, uint32_t n0,
+                                                float* __restrict__ row, const float* sintab) {
+    static_assert(FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "paired moving-cutoff filters");
+    constexpr uint32_t kAll = 0xffffffffu;
+    const bool partner_moves = __shfl_xor_sync(kAll, (int)mv.moving, 1) != 0;      // (every lane runs every shuffle)
+    const bool helper = !mv.moving && partner_moves;
+    auto assigned = [&](float v) { const float t = __shfl_xor_sync(kAll, v, 1); return helper ? t : v; };
+    // the assigned voice: cutoff constants, window, mod-envelope line, frame offset of the first assigned pair
+    CutP cp = mv.cp;
+    cp.lpf = assigned(mv.cp.lpf); cp.amt = assigned(mv.cp.amt); cp.hd = assigned(mv.cp.hd);
+    s2c::Window Wa = W;
+    Wa.xc = assigned(W.xc); Wa.Eh = assigned(W.Eh); Wa.Er = assigned(W.Er); Wa.thc = assigned(W.thc);
+    Wa.Ah = assigned(W.Ah); Wa.Al = assigned(W.Al); Wa.Bh = assigned(W.Bh); Wa.Bl = assigned(W.Bl);
+    const float mes = assigned(mv.mes), mnex0 = assigned(mv.mnex0), mey0 = assigned(mv.mey0);
+    const float xa = __fadd_rn(assigned(__uint2float_rn(n0)), helper ? 2.0f : 0.0f);
+    float2 xa2 = make_float2(xa, __fadd_rn(xa, 1.0f));
+
+    const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
+    uint32_t n = n0;
+    float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
+    FiltS fs = {F.x1, F.x2, F.y1, F.y2};
+    float ph = F.ph;
+#pragma unroll 1
+    for (int j = 0; j < kChunk / 4; j++) {
+        const float2 m2 = s2c::vaddp(pmul2(splat2(mes), padd2(xa2, splat2(mnex0))), splat2(mey0), one);
+        float2 s2, co2;
+        window_frame_sincos<float2>(Wa, cp, one, m2, &s2, &co2);
+        const float2 q2 = s2c::quotient_of<float2>(s2, cp.hd, one);
+        xa2 = padd2(xa2, splat2(4.0f));
+        // the partner's pair: a moving lane receives its frames 4j + 2, 4j + 3
+        const float2 qo = make_float2(__shfl_xor_sync(kAll, q2.x, 1), __shfl_xor_sync(kAll, q2.y, 1));
+        const float2 coo = make_float2(__shfl_xor_sync(kAll, co2.x, 1), __shfl_xor_sync(kAll, co2.y, 1));
+        float o4[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float2 c0, c1, c2;
+            s2c::biquad_from_q_cos<FILTER == FILT_BIQUAD_HP, float2>(h ? qo : q2, h ? coo : co2, one, &c0, &c1, &c2);
+            if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); c2 = splat2(F.c2); }
+            FiltC ca, cb;
+            ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
+            cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
+            const float pa = ph;
+            const float pb = wrap_unit(__fadd_rn(pa, F.d));
+            ph = wrap_unit(__fadd_rn(pb, F.d));
+            const float2 ph2 = make_float2(pa, pb);
+            const float2 osc2 = wave2<KIND>(F, ph2, hbig, kind, sintab);
+            const uint32_t ha = (rot ^ n) * 0x9e3779b9u, hb = (rot ^ (n + 1u)) * 0x9e3779b9u;
+            const float2 u2 = input2<false>(F, osc2, ha, hb);
+            const float2 y2 = filt_step2<FILTER>(u2, ca, cb, fs);
+            const float2 g2 = s2c::vaddp(pmul2(splat2(F.es), padd2(xf2, splat2(F.nex0))), splat2(F.ey0), one);
+            const float2 out2 = TRACE == TRACE_PHASE ? ph2 : pmul2(y2, g2);
+            o4[2 * h] = out2.x;
+            o4[2 * h + 1] = out2.y;
+            n += 2u;
+            xf2 = padd2(xf2, splat2(2.0f));
+        }
+        *reinterpret_cast<float4*>(row + 4 * j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+    F.ph = ph;
+    F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
+}
+
 // Moving-cutoff chunk, one frame at a time: any alignment, any filter, windows made on demand (valid or not).
 // The chunk lies inside one segment `sm` of the mod envelope.  The same per-frame functions as the packed form,
 // hence the same bits.

@@ -49,7 +49,8 @@ struct RenderArgs {
     uint32_t has_sine;     // any voice uses the table oscillator -> stage SIN_TABLE in smem
     float one;             // 1.0f, opaque to the compiler (s2_cutoff.h: vaddp)
     uint32_t force_path;   // test hook (S2_FORCE_PATH): 0 = normal, 1 = moving-cutoff chunks one frame at a time,
-                           // 2 = every chunk through the general per-frame path
+                           // 2 = every chunk through the general per-frame path, 3 = packed moving-cutoff chunks
+                           // without the lane-pair help (chunk_modcut_pk only)
 };
 
 constexpr int kWarpsPerBlock = 1;

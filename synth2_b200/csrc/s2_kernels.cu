@@ -427,15 +427,29 @@ render_kernel(const RenderArgs a) {
                                 ok = W.valid != 0u;
                             }
                         }
-                        packed = a.force_path == 0u && __all_sync(0xffffffffu, ok);
+                        packed = (a.force_path == 0u || a.force_path == 3u) && __all_sync(0xffffffffu, ok);
                     }
                     if (packed) {
                         if constexpr (kPackable) {
                             if (edge) { F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f; }
-                            switch (wkind) {
-                            case 0: chunk_modcut_pk<FILTER, 0, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
-                            case 1: chunk_modcut_pk<FILTER, 1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
-                            default: chunk_modcut_pk<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                            // no lane pair (2i, 2i + 1) with two moving lanes: the resting lane of a pair helps
+                            const uint32_t mmask = __ballot_sync(0xffffffffu, mv.moving);
+                            bool paired = false;
+                            if constexpr (FILTER != FILT_ONE_POLE) paired = (mmask & (mmask >> 1) & 0x55555555u) == 0u && a.force_path != 3u;
+                            if (paired) {
+                                if constexpr (FILTER != FILT_ONE_POLE) {
+                                    switch (wkind) {
+                                    case 0: chunk_modcut_pr<FILTER, 0, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                    case 1: chunk_modcut_pr<FILTER, 1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                    default: chunk_modcut_pr<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                    }
+                                }
+                            } else {
+                                switch (wkind) {
+                                case 0: chunk_modcut_pk<FILTER, 0, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                case 1: chunk_modcut_pk<FILTER, 1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                default: chunk_modcut_pk<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
+                                }
                             }
                             if (TRACE != TRACE_PHASE && edge) edge_gain(&C.amp, crow, n);
                         }

@@ -471,7 +471,8 @@ def test_split_invariance_bitwise():
 @pytest.mark.parametrize("filter_kind", [0, 1, 2, 4])
 def test_paths_agree_bitwise(filter_kind, monkeypatch):
     """Purity of the per-frame functions (s2_cutoff.h): the specialised paths of the render kernel — fast tiles,
-    packed moving-cutoff chunks, one-frame-at-a-time moving-cutoff chunks — and the general per-frame path
+    packed moving-cutoff chunks with the resting lane of a pair helping its moving partner (default) and without
+    (S2_FORCE_PATH=3), one-frame-at-a-time moving-cutoff chunks (1) — and the general per-frame path
     (S2_FORCE_PATH=2) perform the same IEEE operations per frame: identical bits, including through envelope
     ramps, moving cutoffs (window-aligned and not), pitch modulation and the scalar tail."""
     frames = [4096, 4096, 2048, 1000]
@@ -483,13 +484,13 @@ def test_paths_agree_bitwise(filter_kind, monkeypatch):
     v["frame_offset"][96:] = 16 * (np.arange(64) % 5)
     v["release_offset"] = 6000
     outs = {}
-    for path in ("0", "1", "2"):
+    for path in ("0", "1", "2", "3"):
         monkeypatch.setenv("S2_FORCE_PATH", path)
         outs[path] = gpu_bank_render(v, filter_kind, frames)
     monkeypatch.delenv("S2_FORCE_PATH")
     a = outs["2"]
     assert np.all(np.isfinite(a[0]))
-    for name in ("0", "1"):
+    for name in ("0", "1", "3"):
         b = outs[name]
         bad = np.argwhere(a[0] != b[0])
         assert bad.size == 0, f"path {name}: first differing (voice, frame): {bad[:5].tolist()}"
