@@ -893,22 +893,6 @@ __device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvQ* __restrict
     F.x1 = fs.x1; F.x2 = fs.x2; F.y1 = fs.y1; F.y2 = fs.y2;
 }
 
-// The amp envelope of a lane whose segment ends inside a chunk that ran with a gain of exactly 1 (the packed loops
-// take the envelope as one line): out = RN(y * g), as every other path rounds it.
-static __device__ __noinline__ void edge_gain(const EnvQ* __restrict__ amp, float* __restrict__ row, uint32_t n0) {
-    SegEnv sa = seg_env(*amp, n0);
-    uint32_t n = n0;
-    float xf = __uint2float_rn(n0);
-#pragma unroll 1
-    for (int i = 0; i < kChunk; i++) {
-        float g;
-        if (n < sa.nend) g = seg_eval(sa, xf); else { g = env_x16(*amp, xf); sa = seg_env(*amp, n + 1u); }
-        row[i] = __fmul_rn(row[i], g);
-        n += 1u;
-        xf = __fadd_rn(xf, 1.0f);
-    }
-}
-
 // One frame per lane: the filter coefficients of frames n0 .. n0 + 31 of a cutoff trajectory shared by the warp.
 template <int FILTER>
 __device__ __forceinline__ void modcut_coefficients(const SegEnv& sm, const CutP& cp, float one, uint32_t n0, int lane,

@@ -254,6 +254,24 @@ render_kernel(const RenderArgs a) {
             if (lane < 16) *reinterpret_cast<float4*>(bus_row() + ts + c4) = make_float4(s01.x, s01.y, s23.x, s23.y);
         }
     };
+    // The amp envelope of the lanes whose segment ends inside a chunk that ran with a gain of exactly 1 (the packed
+    // loops take the envelope as one line): out = RN(y * g), as every other path rounds it.  The warp does one such
+    // lane at a time, one frame per lane, from that lane's envelope in shared memory.  `h` = the chunk's first
+    // column of the tile, `n0` = each lane's own frame offset at the chunk's start.
+    auto edge_gain = [&](bool edge, uint32_t h, uint32_t n0) {
+        uint32_t em = __ballot_sync(0xffffffffu, edge);
+        if (em == 0u) return;
+        __syncwarp();
+        while (em) {
+            const int l = __ffs(em) - 1;
+            em &= em - 1u;
+            const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + l * kColdWords);
+            const uint32_t nl = __shfl_sync(0xffffffffu, n0, l);
+            float* r = tile + l * kTileStride + h + lane;
+            *r = __fmul_rn(*r, env_x16(CL.amp, __uint2float_rn(nl + (uint32_t)lane)));
+        }
+        __syncwarp();
+    };
     auto clear_chunk = [&](float* r) {
 #pragma unroll
         for (int j = 0; j < kChunk / 4; j++)
@@ -362,7 +380,7 @@ render_kernel(const RenderArgs a) {
                     case 3: fast_tile<FILTER, 3, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
                     default: fast_tile<FILTER, -1, TRACE>(gmode, fasthash, F, &C.amp, one, kind, rot, n, row + hh, sintab); break;
                     }
-                    if (TRACE != TRACE_PHASE && edge) edge_gain(&C.amp, row + hh, n);
+                    if (TRACE != TRACE_PHASE && seg_left < (uint32_t)kChunk) edge_gain(edge, hh, n);
                     n += kChunk;
                     hh += (uint32_t)kChunk;
                     if (reps && hh == kTile) {
@@ -451,7 +469,7 @@ render_kernel(const RenderArgs a) {
                                 default: chunk_modcut_pk<FILTER, -1, TRACE>(F, mv, W, one, kind, rot, n, crow, sintab); break;
                                 }
                             }
-                            if (TRACE != TRACE_PHASE && edge) edge_gain(&C.amp, crow, n);
+                            if (TRACE != TRACE_PHASE) edge_gain(edge, h0, n);
                         }
                     } else {
                         chunk_modcut_sc<FILTER, -1, TRACE, false>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, nullptr);
