@@ -49,7 +49,6 @@ struct OscC {                // everything derived from the period; hoisting a d
 
 struct FiltC {               // one-pole: c0 = k, c1 = 1 - k.   biquad: c0 = 2*alpha, c1 = 2*beta, c2 = 2*gamma
     float c0, c1, c2;
-    float co;                // second-order low-pass / high-pass: cos(theta) the coefficients were made from (resting only)
     uint32_t fl_bits;
 };
 
@@ -211,7 +210,6 @@ __device__ __forceinline__ void make_filt_theta(FiltC& c, float th, float damp) 
         c.c0 = __fmul_rn(2.0f, alpha);
         c.c1 = __fmul_rn(2.0f, beta);
         c.c2 = __fmul_rn(2.0f, gamma);
-        c.co = co;
     } else if (FILTER == FILT_BIQUAD_BP) {
         // try3/dsp_filters.rs:197-207; `damp` carries the quality factor
         const float tn = s2_tanf(__fdiv_rn(th, __fmul_rn(2.0f, damp)));
@@ -249,9 +247,7 @@ __device__ __forceinline__ void make_filt(FiltC& c, float fl, float damp, float 
         c.c0 = k;
         c.c1 = __fsub_rn(1.0f, k);
         c.c2 = 0.0f;
-        c.co = 0.0f;
     } else {
-        c.co = 0.0f;
         make_filt_theta<FILTER>(c, theta_ref(fl, sr), damp);
     }
 }
@@ -643,7 +639,7 @@ __device__ __forceinline__ void chunk_fast_tp(FastV& F, const EnvQ* __restrict__
     if (GMODE == G_ANY) sg = seg_env(*amp, n0);
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
-    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.co = 0.0f; fc.fl_bits = 0;
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
     float ph = F.ph;
     // 8 frames per trip: long enough to overlap neighbouring frames, short enough for the instruction cache
 #pragma unroll 1
@@ -734,17 +730,11 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
 #pragma unroll 1
     for (int j = 0; j < kChunk / 4; j++) {
         float o4[4];
-#ifdef S2_EXP_HALFCOEF
-        float2 kc0 = splat2(0.0f), kc1 = kc0, kc2 = kc0;
-#endif
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             // the mod envelope's line at the two frame offsets
             const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
             float2 c0, c1, c2;
-#ifdef S2_EXP_HALFCOEF
-            if (h == 1) { c0 = kc0; c1 = kc1; c2 = kc2; } else
-#endif
             if (FILTER == FILT_ONE_POLE) {
                 c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
                 c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
@@ -756,9 +746,6 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
                 s2c::biquad_lp_hp<FILTER == FILT_BIQUAD_HP, float2>(s2, co2, mv.cp.hd, one, &c0, &c1, &c2);
                 if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); c2 = splat2(F.c2); }
             }
-#ifdef S2_EXP_HALFCOEF
-            kc0 = c0; kc1 = c1; kc2 = c2;
-#endif
             FiltC ca, cb;
             ca.c0 = c0.x; ca.c1 = c1.x; ca.c2 = c2.x;
             cb.c0 = c0.y; cb.c1 = c1.y; cb.c2 = c2.y;
@@ -868,7 +855,7 @@ __device__ __forceinline__ void chunk_modcut_sc(FastV& F, const EnvQ* __restrict
     o.P = F.P; o.d = F.d; o.slope = F.slope; o.half = -F.nhalf; o.ts1 = F.ts1; o.ts2 = F.ts2; o.fo_bits = 0;
     FiltS fs = {F.x1, F.x2, F.y1, F.y2};
     FiltC fc;
-    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.co = 0.0f; fc.fl_bits = 0;
+    fc.c0 = F.c0; fc.c1 = F.c1; fc.c2 = F.c2; fc.fl_bits = 0;
     s2c::Window W;
     window_none(W);
     float ph = F.ph;

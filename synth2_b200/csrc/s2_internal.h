@@ -27,7 +27,7 @@ enum StateIdx {
     // exp / sin / cos in binary64), keyed by the exact input bits: a launch that finds its key reuses
     // them instead of re-deriving ~1000 instructions per voice.  Not part of s2_voice_state.
     S_FO_KEY, S_OSC_P, S_OSC_D, S_OSC_SLOPE, S_OSC_HALF, S_OSC_TS1, S_OSC_TS2,
-    S_FL_KEY, S_DAMP_KEY, S_FC_C0, S_FC_C1, S_FC_C2, S_FC_CO,
+    S_FL_KEY, S_DAMP_KEY, S_FC_C0, S_FC_C1, S_FC_C2,
     S_COUNT
 };
 constexpr uint32_t kNoKey = 0x7fc00001u;   // a NaN payload no frequency can have

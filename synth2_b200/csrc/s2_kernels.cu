@@ -129,7 +129,7 @@ render_kernel(const RenderArgs a) {
         C.oc = oc;
         FiltC fc;
         fc.fl_bits = __float_as_uint(S[S_DAMP_KEY * vp]) == __float_as_uint(L.damp) ? __float_as_uint(S[S_FL_KEY * vp]) : kNoKey;
-        fc.c0 = S[S_FC_C0 * vp]; fc.c1 = S[S_FC_C1 * vp]; fc.c2 = S[S_FC_C2 * vp]; fc.co = S[S_FC_CO * vp];
+        fc.c0 = S[S_FC_C0 * vp]; fc.c1 = S[S_FC_C1 * vp]; fc.c2 = S[S_FC_C2 * vp];
         C.fc = fc;
         C.n_safe = 0u;
         C.msg.es = C.msg.nex0 = C.msg.ey0 = 0.0f; C.msg.nbeg = 1u; C.msg.nend = 0u; C.msg.stage = 4;
@@ -564,7 +564,7 @@ render_kernel(const RenderArgs a) {
         S[S_OSC_HALF * vp] = oc.half; S[S_OSC_TS1 * vp] = oc.ts1; S[S_OSC_TS2 * vp] = oc.ts2;
         S[S_FL_KEY * vp] = __uint_as_float(fc.fl_bits);
         S[S_DAMP_KEY * vp] = C.damp;
-        S[S_FC_C0 * vp] = fc.c0; S[S_FC_C1 * vp] = fc.c1; S[S_FC_C2 * vp] = fc.c2; S[S_FC_CO * vp] = fc.co;
+        S[S_FC_C0 * vp] = fc.c0; S[S_FC_C1 * vp] = fc.c1; S[S_FC_C2 * vp] = fc.c2;
     }
 }
 
