@@ -498,6 +498,31 @@ def test_paths_agree_bitwise(filter_kind, monkeypatch):
         assert a[1].tobytes() == b[1].tobytes()
 
 
+@pytest.mark.parametrize("followers", [0.0, 0.2, 0.8, 1.0])
+def test_lane_pair_layouts_agree_bitwise(followers, monkeypatch):
+    """s2_bank_create pairs voices whose cutoff follows the mod envelope with voices whose cutoff rests (aligned
+    lane pairs, chunk_modcut_pr); with few or many followers some voices find no partner and whole warps fall back
+    to chunk_modcut_pk.  Whatever the proportion, the output is the general per-frame path's (S2_FORCE_PATH=2) bit
+    for bit, in the caller's voice order, and within the bar of the oracle."""
+    frames = [4096, 4096, 2048]
+    n = 333                                           # ragged last warp, odd group sizes
+    v = bank_for(1, n, sum(frames), kinds=(0, 1, 2))
+    rng = np.random.default_rng(int(followers * 10) + 7)
+    v["mod_env_to_lpf_freq"] = np.where(rng.uniform(size=n) < followers, 1.5, 0.0).astype(np.float32)
+    v["active"][5::41] = 0
+    outs = {}
+    for path in ("0", "2"):
+        monkeypatch.setenv("S2_FORCE_PATH", path)
+        outs[path] = gpu_bank_render(v, 1, frames)
+    monkeypatch.delenv("S2_FORCE_PATH")
+    a, b = outs["0"], outs["2"]
+    bad = np.argwhere(a[0] != b[0])
+    assert bad.size == 0, f"first differing (voice, frame): {bad[:5].tolist()}"
+    assert a[2].tobytes() == b[2].tobytes()
+    ref, _, _ = oracle_bank_render(v, 1, frames)
+    assert_parity(ref, a[0], f"lane pairs, {followers:.0%} followers")
+
+
 @pytest.mark.parametrize("n_sub", [2, 4, 8])
 def test_pipelined_sub_banks_agree_bitwise(n_sub):
     """s2_bank_set_pipeline: the same voices rendered as n_sub ranges on internal streams give the same
