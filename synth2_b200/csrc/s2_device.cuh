@@ -717,11 +717,14 @@ struct MovV {
 // classifier, the window's binary64 code, this loop and the write-back once per chunk, and with 8-frame trips in
 // four variants that path outgrew the 32 KB instruction cache of an SM — 41 % of the stall samples of such a launch
 // were instruction fetch (profiles/r2_notes.md).
-template <int FILTER, int KIND, int TRACE>
+// SHARED: the warp's voices share one cutoff trajectory and the chunk's 32 coefficient sets are in `ctab`
+// ([c0 | c1 | c2][32], modcut_coefficients): the loop reads them, two frames per load, instead of evaluating them.
+template <int FILTER, int KIND, int TRACE, bool SHARED = false>
 __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const s2c::Window& W,
                                                 float one, uint32_t kind, uint32_t rot, uint32_t n0,
-                                                float* __restrict__ row, const float* sintab) {
-    static_assert(FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
+                                                float* __restrict__ row, const float* sintab,
+                                                const float* __restrict__ ctab = nullptr) {
+    static_assert(SHARED || FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP, "packed moving-cutoff filters");
     const float hbig = __fmul_rn(-F.nhalf, 0x1p60f);
     uint32_t n = n0;
     float2 xf2 = make_float2(__uint2float_rn(n0), __uint2float_rn(n0 + 1u));
@@ -735,7 +738,12 @@ __device__ __forceinline__ void chunk_modcut_pk(FastV& F, const MovV& mv, const 
             // the mod envelope's line at the two frame offsets
             const float2 m2 = s2c::vaddp(pmul2(splat2(mv.mes), padd2(xf2, splat2(mv.mnex0))), splat2(mv.mey0), one);
             float2 c0, c1, c2;
-            if (FILTER == FILT_ONE_POLE) {
+            if (SHARED) {
+                c0 = *reinterpret_cast<const float2*>(ctab + 4 * j + 2 * h);
+                c1 = *reinterpret_cast<const float2*>(ctab + 32 + 4 * j + 2 * h);
+                c2 = *reinterpret_cast<const float2*>(ctab + 64 + 4 * j + 2 * h);
+                if (!mv.moving) { c0 = splat2(F.c0); c1 = splat2(F.c1); c2 = splat2(F.c2); }
+            } else if (FILTER == FILT_ONE_POLE) {
                 c0 = s2c::exp_neg_fast<float2>(s2c::theta_at<float2>(m2, mv.cp.amt, mv.cp.theta0));
                 c1 = pfma2(c0, splat2(-one), splat2(1.0f));               // 1 - k, one rounding (exact product)
                 c2 = splat2(0.0f);

@@ -407,19 +407,38 @@ render_kernel(const RenderArgs a) {
                 SegEnv sm = C.msg;
                 mv.mes = sm.es; mv.mnex0 = sm.nex0; mv.mey0 = sm.ey0;
                 constexpr bool kPackable = FILTER == FILT_ONE_POLE || FILTER == FILT_BIQUAD_LP || FILTER == FILT_BIQUAD_HP;
+                // the packed forms take the amp envelope as one line through the chunk (as G_LINE); a lane with a stage
+                // boundary inside the chunk takes a gain of 1 and edge_gain afterwards
+                auto amp_line = [&]() {
+                    if (active && n >= F.seg_end) {
+                        const SegEnv sg = seg_env(C.amp, n);
+                        F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
+                        lane_gconst = sg.stage == 2 || sg.stage == 4;
+                    }
+                    return active && F.seg_end - n < (uint32_t)kChunk;
+                };
                 if (filt_uniform) {
-                    // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once
+                    // one cutoff trajectory for the whole warp: 32 frames' coefficients, one per lane, once; the
+                    // packed loop reads them
                     const Cold& CL = *reinterpret_cast<const Cold*>(cold_base + leader * kColdWords);
                     const uint32_t n_lead = __shfl_sync(0xffffffffu, n, leader);   // inactive lanes hold other offsets
                     const CutP cpl = cutp_of(CL.lpf, CL.theta0, CL.amt_lpf, CL.damp, sr, rsr);
                     const SegEnv sml = CL.msg;
                     modcut_coefficients<FILTER>(sml, cpl, one, n_lead, lane, ctab);
                     __syncwarp();
-                    switch (wkind) {
-                    case 0: chunk_modcut_sc<FILTER, 0, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
-                    case 1: chunk_modcut_sc<FILTER, 1, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
-                    case 2: chunk_modcut_sc<FILTER, 2, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
-                    default: chunk_modcut_sc<FILTER, -1, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab); break;
+                    if (a.force_path == 0u || a.force_path == 3u) {
+                        const bool edge = amp_line();
+                        if (edge) { F.es = 0.0f; F.nex0 = 0.0f; F.ey0 = 1.0f; }
+                        s2c::Window W;
+                        window_none(W);
+                        switch (wkind) {
+                        case 0: chunk_modcut_pk<FILTER, 0, TRACE, true>(F, mv, W, one, kind, rot, n, crow, sintab, ctab); break;
+                        case 1: chunk_modcut_pk<FILTER, 1, TRACE, true>(F, mv, W, one, kind, rot, n, crow, sintab, ctab); break;
+                        default: chunk_modcut_pk<FILTER, -1, TRACE, true>(F, mv, W, one, kind, rot, n, crow, sintab, ctab); break;
+                        }
+                        if (TRACE != TRACE_PHASE) edge_gain(edge, h0, n);
+                    } else {
+                        chunk_modcut_sc<FILTER, -1, TRACE, true>(F, &C.amp, mv, sm, one, kind, rot, n, crow, sintab, ctab);
                     }
                     __syncwarp();          // ctab is rewritten by the next moving-cutoff chunk
                 } else {
@@ -429,14 +448,7 @@ render_kernel(const RenderArgs a) {
                     s2c::Window W;
                     window_none(W);
                     if constexpr (kPackable) {
-                        // the packed form takes the amp envelope as one line through the chunk (as G_LINE); a lane with
-                        // a stage boundary inside the chunk takes a gain of 1 and edge_gain afterwards
-                        if (active && n >= F.seg_end) {
-                            const SegEnv sg = seg_env(C.amp, n);
-                            F.es = sg.es; F.nex0 = sg.nex0; F.ey0 = sg.ey0; F.seg_end = sg.nend;
-                            lane_gconst = sg.stage == 2 || sg.stage == 4;
-                        }
-                        edge = active && F.seg_end - n < (uint32_t)kChunk;
+                        edge = amp_line();
                         bool ok = true;
                         if (mv.moving) {
                             ok = (n & 31u) == 0u;
