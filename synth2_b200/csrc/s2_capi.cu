@@ -149,6 +149,7 @@ struct s2_bank {
     float* d_state = nullptr;
     float* d_partials = nullptr;
     size_t partials_cap = 0;     // floats
+    unsigned int* d_bus_counters = nullptr;   // s2::kBusCounters zeroed words of the wide bus reduction
     float* d_bus = nullptr;
     size_t bus_cap = 0;          // floats
     std::vector<VoiceBook> book;  // indexed by voice
@@ -278,7 +279,7 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
             CUDA_TRY(cudaMemcpyAsync(d_bus_out, partials, frames * sizeof(float), cudaMemcpyDeviceToDevice, b->mix));
         } else {
             CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
-                                           d_bus_out, b->mix));
+                                           d_bus_out, b->mix, b->d_bus_counters, (size_t)s2::bus_segments(n_warps) * frames));
             g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         CUDA_TRY(cudaEventRecord(b->ev_mix[p], b->mix));
@@ -447,7 +448,7 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {
         CUDA_TRY(s2::launch_bus_reduce(partials, n_warps, frames, (uint32_t)frames, partials + (size_t)n_warps * frames,
-                                       d_bus_out, b->stream));
+                                       d_bus_out, b->stream, b->d_bus_counters, (size_t)s2::bus_segments(n_warps) * frames));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     b->total_frames += frames;
@@ -620,6 +621,8 @@ int s2_bank_create(int device, uint32_t sample_rate, uint32_t filter_kind, size_
     }
     cudaError_t e = cudaMalloc(&b->d_params, hp.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_state, hs.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_bus_counters, s2::kBusCounters * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_bus_counters, 0, s2::kBusCounters * sizeof(unsigned int), b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_params, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_state, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
@@ -640,6 +643,7 @@ void s2_bank_destroy(s2_bank* b) {
     cudaFree(b->d_params);
     cudaFree(b->d_state);
     cudaFree(b->d_partials);
+    cudaFree(b->d_bus_counters);
     cudaFree(b->d_bus);
     cudaFree(b->d_stage);
     for (int k = 0; k < 8; k++) {

@@ -623,6 +623,61 @@ __global__ void __launch_bounds__(256) bus_reduce_kernel(const float* __restrict
     }
 }
 
+// The same reduction for wide banks, four frames per lane: block (fx, rs) owns 128 frames and a quarter of the
+// partial rows; its 8 warps take the rows w, w + 8, ... of that quarter with 16-byte loads (512 contiguous bytes per
+// warp and row, four rows in flight per lane: four times the bytes in flight of the form above, a quarter of its
+// instructions), the quarter's sum goes to `scratch[rs]`, and the last of the four blocks to finish adds the four
+// quarters in index order — a fixed order whichever block that is.  It shares the machine with the render blocks of
+// the next step for a third of the time the one-frame-per-lane form needs.
+constexpr uint32_t kRedSplit = 4;
+
+__global__ void __launch_bounds__(256, 8) bus_reduce_wide_kernel(const float* __restrict__ partials, uint32_t n_rows,
+                                                              size_t row_stride, uint32_t frames, float* scratch,
+                                                              unsigned int* counters, float* __restrict__ bus) {
+    __shared__ float4 sm[8][32];
+    __shared__ bool last;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t fx = blockIdx.x / kRedSplit, rs = blockIdx.x % kRedSplit;
+    const uint32_t t = fx * 128u + 4u * lane;
+    const uint32_t r1 = (uint32_t)((uint64_t)n_rows * (rs + 1u) / kRedSplit);
+    uint32_t r = (uint32_t)((uint64_t)n_rows * rs / kRedSplit) + w;
+    auto add4 = [](float4 a, float4 v) {
+        return make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
+    };
+    float4 a0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), a1 = a0;
+    const float* __restrict__ col = partials + t;
+    for (; r + 24u < r1; r += 32u) {                        // rows r, r + 8, r + 16, r + 24 in flight
+        float4 v[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++) v[k] = __ldcs(reinterpret_cast<const float4*>(col + (size_t)(r + 8u * k) * row_stride));
+        a0 = add4(a0, v[0]); a1 = add4(a1, v[1]); a0 = add4(a0, v[2]); a1 = add4(a1, v[3]);
+    }
+    for (uint32_t k = 0; r < r1; r += 8u, k++) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(col + (size_t)r * row_stride));
+        if (k & 1u) a1 = add4(a1, v); else a0 = add4(a0, v);
+    }
+    sm[w][lane] = add4(a0, a1);
+    __syncthreads();
+    if (w == 0) {
+        float4 total = sm[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; k++) total = add4(total, sm[k][lane]);
+        __stcg(reinterpret_cast<float4*>(scratch + (size_t)rs * frames + t), total);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&counters[fx], 1u) == kRedSplit - 1u;
+    __syncthreads();
+    if (last && w == 0) {
+        __threadfence();
+        float4 total = __ldcg(reinterpret_cast<const float4*>(scratch + t));
+#pragma unroll
+        for (uint32_t k = 1; k < kRedSplit; k++) total = add4(total, __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)k * frames + t)));
+        *reinterpret_cast<float4*>(bus + t) = total;
+        if (lane == 0) counters[fx] = 0u;                  // ready for the next launch (same stream)
+    }
+}
+
 __global__ void gather_u32_kernel(const uint32_t* __restrict__ staged, const float* __restrict__ row_index_bits,
                                   uint32_t* __restrict__ dst, uint32_t n) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -671,9 +726,18 @@ cudaError_t launch_render(const RenderArgs& a, uint32_t filter_kind, int trace, 
 uint32_t bus_segments(uint32_t n_warps) { return (n_warps + kBusSegWarps - 1) / kBusSegWarps; }
 
 cudaError_t launch_bus_reduce(const float* partials, uint32_t n_warps, size_t row_stride, uint32_t frames,
-                              float* /*seg_scratch*/, float* bus, cudaStream_t stream) {
+                              float* scratch, float* bus, cudaStream_t stream, unsigned int* counters,
+                              size_t scratch_floats) {
     if (frames == 0) return cudaSuccess;
-    bus_reduce_kernel<<<(frames + 31) / 32, 256, 0, stream>>>(partials, n_warps, row_stride, frames, bus);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0u; };
+    const bool wide = counters != nullptr && n_warps >= 512u && (frames & 127u) == 0u && frames / 128u <= kBusCounters &&
+                      (row_stride & 3u) == 0u && scratch_floats >= (size_t)kRedSplit * frames &&
+                      al16(partials) && al16(scratch) && al16(bus);
+    if (wide)
+        bus_reduce_wide_kernel<<<frames / 128u * kRedSplit, 256, 0, stream>>>(partials, n_warps, row_stride, frames, scratch,
+                                                                              counters, bus);
+    else
+        bus_reduce_kernel<<<(frames + 31) / 32, 256, 0, stream>>>(partials, n_warps, row_stride, frames, bus);
     return cudaGetLastError();
 }
 
