@@ -252,24 +252,27 @@ int bank_render_pipelined(s2_bank* b, size_t frames, float* d_voice_out, size_t 
     a.has_sine = b->n_sine ? 1u : 0u;
     a.one = 1.0f;
     a.force_path = b->force_path;
+    a.staged_release = nullptr;
+    a.release_row = nullptr;
     uint32_t* release_row = reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad);
     for (int k = 0; k < b->n_sub; k++) {
         a.slot_begin = sub_begin(b, k);
         a.slot_end = sub_begin(b, k + 1);
         if (a.slot_begin >= a.slot_end) continue;
         cudaStream_t sk = b->sub[k];
+        a.staged_release = nullptr;
+        a.release_row = nullptr;
         if (b->table_pending >= 0) {
-            // apply the staged note-off table to this sub-bank's slots, ordered between its own renders
+            // the staged note-off table: this sub-bank's render applies it to its own slots first (kernel prologue),
+            // ordered between its own renders
             CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_stage[b->table_pending], 0));
-            CUDA_TRY(s2::launch_gather_u32(b->d_stage2[b->table_pending],
-                                           b->d_params + (size_t)s2::P_ROW * b->vpad + a.slot_begin,
-                                           release_row + a.slot_begin, a.slot_end - a.slot_begin, sk));
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            CUDA_TRY(cudaEventRecord(b->ev_gather[k][b->table_pending], sk));
+            a.staged_release = b->d_stage2[b->table_pending];
+            a.release_row = release_row;
         }
         if (d_bus_out && b->step >= (uint64_t)kMixBufs) CUDA_TRY(cudaStreamWaitEvent(sk, b->ev_mix[p], 0));   // partials[p] are free again
         CUDA_TRY(s2::launch_render(a, b->filter_kind, s2::TRACE_NONE, sk));
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (b->table_pending >= 0) CUDA_TRY(cudaEventRecord(b->ev_gather[k][b->table_pending], sk));   // staging buffer read
         CUDA_TRY(cudaEventRecord(b->ev_sub[k], sk));
     }
     b->table_pending = -1;
@@ -345,6 +348,8 @@ int bank_render_time_split(s2_bank* b, size_t frames, float* d_voice_out, size_t
     a.has_sine = b->n_sine ? 1u : 0u;
     a.one = 1.0f;
     a.force_path = b->force_path;
+    a.staged_release = nullptr;
+    a.release_row = nullptr;
     if (b->ts_main_dirty) {
         // the pre-pass reads the carried phase: order it after whatever the bank's stream wrote
         CUDA_TRY(cudaEventRecord(b->ev_main, b->stream));
@@ -444,6 +449,8 @@ int bank_render_impl(s2_bank* b, size_t frames, float* d_voice_out, size_t row_s
     a.has_sine = b->n_sine ? 1u : 0u;
     a.one = 1.0f;
     a.force_path = b->force_path;
+    a.staged_release = nullptr;
+    a.release_row = nullptr;
     CUDA_TRY(s2::launch_render(a, b->filter_kind, trace, b->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (d_bus_out && n_warps > 1) {

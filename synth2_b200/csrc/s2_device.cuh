@@ -382,7 +382,7 @@ struct EnvQ { float A, AD, S, Rs, E, sA, sD, sR; };
 __device__ __forceinline__ EnvQ compact(const EnvP& e) { return {e.A, e.AD, e.S, e.Rs, e.E, e.sA, e.sD, e.sR}; }
 
 // Decode one voice's parameter column (struct-of-arrays, see s2_internal.h).
-__device__ __forceinline__ Lane load_lane(const float* __restrict__ P, uint32_t vp, float sr) {
+__device__ __forceinline__ Lane load_lane(const float* __restrict__ P, uint32_t vp, float sr, uint32_t release) {
     Lane L;
     L.kind = __float_as_uint(P[P_KIND * vp]);
     const uint32_t seed = __float_as_uint(P[P_SEED * vp]);
@@ -394,7 +394,6 @@ __device__ __forceinline__ Lane load_lane(const float* __restrict__ P, uint32_t 
     L.damp = P[P_DAMP * vp];
     L.amt_osc = P[P_AMT_OSC * vp];
     L.amt_lpf = P[P_AMT_LPF * vp];
-    const uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
     make_env(L.amp, P[P_AA * vp], P[P_AD * vp], P[P_AS * vp], P[P_AR * vp], release, sr);
     make_env(L.mod, P[P_MA * vp], P[P_MD * vp], P[P_MS * vp], P[P_MR * vp], release, sr);
     return L;
@@ -970,6 +969,7 @@ struct Cold {
     OscC oc;
     FiltC fc;
     SegEnv msg;            // the mod-envelope ramp the voice's moving cutoff is in (flags bit 2)
+    uint32_t release;      // release offset in force for this launch (the parameter row or a staged note-off table)
     uint32_t n_safe;       // the resting constants (period, cutoff) are valid for frame offsets [.., n_safe)
     uint32_t vi;           // slot index (state/params column)
     uint32_t out_row;      // caller-visible voice index, 0xffffffff = no such voice

@@ -48,6 +48,10 @@ struct RenderArgs {
     float* bus_partials;   // [n_warps][frames] or nullptr
     uint32_t has_sine;     // any voice uses the table oscillator -> stage SIN_TABLE in smem
     float one;             // 1.0f, opaque to the compiler (s2_cutoff.h: vaddp)
+    // A staged note-off table to apply first (pipelined banks): release offset of slot s = staged_release[caller's
+    // voice index of s], also written to release_row[s] so that it persists.  nullptr = the parameter row as it is.
+    const uint32_t* staged_release;
+    uint32_t* release_row;
     uint32_t force_path;   // test hook (S2_FORCE_PATH): 0 = normal, 1 = moving-cutoff chunks one frame at a time,
                            // 2 = every chunk through the general per-frame path, 3 = packed moving-cutoff chunks
                            // without the lane-pair help (chunk_modcut_pk only)

@@ -101,7 +101,13 @@ render_kernel(const RenderArgs a) {
         active = exists && __float_as_uint(P[P_ACTIVE * vp]) != 0u;
         C.vi = vi;
         C.out_row = exists ? __float_as_uint(P[P_ROW * vp]) : 0xffffffffu;
-        const Lane L = load_lane(P, vp, sr);
+        uint32_t release = __float_as_uint(P[P_RELEASE * vp]);
+        if (a.staged_release != nullptr && exists) {
+            release = a.staged_release[C.out_row];
+            a.release_row[vi] = release;
+        }
+        C.release = release;
+        const Lane L = load_lane(P, vp, sr, release);
         kind = L.kind;
         rot = L.rot;
         C.amp = compact(L.amp);
@@ -493,7 +499,7 @@ render_kernel(const RenderArgs a) {
             } else {
                 if (active) {
                     // the general path derives everything again from the voice's parameter column
-                    const Lane L = load_lane(a.params + C.vi, vp, sr);
+                    const Lane L = load_lane(a.params + C.vi, vp, sr, C.release);
                     OscC oc = C.oc;
                     FiltC fc = C.fc;
                     MovG mg;
