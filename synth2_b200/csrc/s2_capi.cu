@@ -852,6 +852,15 @@ int s2_bank_set_pipeline(s2_bank* b, int n_sub) {
     if (n_sub > 1 && b->ts_enabled) return fail(S2_ERR_INVALID, "time-split and pipelined voice ranges are exclusive");
     CUDA_TRY(cudaSetDevice(b->device));
     { int rc = s2_bank_sync(b); if (rc) return rc; }
+    if (b->n_sub > 1 && b->table_pending >= 0) {
+        // a note-off table staged for the next pipelined render: apply it now, the ranges are about to change
+        CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_stage[b->table_pending], 0));
+        CUDA_TRY(s2::launch_gather_u32(b->d_stage2[b->table_pending], b->d_params + (size_t)s2::P_ROW * b->vpad,
+                                       reinterpret_cast<uint32_t*>(b->d_params + (size_t)s2::P_RELEASE * b->vpad),
+                                       (uint32_t)b->n_voices, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        b->table_pending = -1;
+    }
     if (n_sub > 1) {
         for (int k = 0; k < n_sub; k++) {
             if (!b->sub[k]) CUDA_TRY(cudaStreamCreateWithFlags(&b->sub[k], cudaStreamNonBlocking));

@@ -567,6 +567,39 @@ def test_pipelined_sub_banks_agree_bitwise(n_sub):
     assert_parity(np.concatenate([o0, o1], axis=1), b[0][:, :frames[0] + frames[1]], "pipelined vs oracle")
 
 
+def test_note_off_table_survives_a_pipeline_change():
+    """A note-off table staged for the next pipelined render (the render kernels of the ranges apply it in their
+    prologues) is not lost when the number of ranges changes first, or when the bank goes back to one stream."""
+    frames = [2048, 4096]
+    V = 500
+    v = bank_for(1, V, sum(frames), kinds=(0, 1))
+    v["release_offset"] = s2.NO_RELEASE
+    rel = np.full(V, s2.NO_RELEASE, dtype=np.uint32)
+    rel[::2] = 3000
+
+    def run(first, second):
+        with s2.VoiceBank(v, SR, 1) as bank:
+            if first > 1:
+                bank.set_pipeline(first)
+            outs = []
+            for i, fr in enumerate(frames):
+                if i == 1:
+                    bank.set_releases(rel)
+                    if second != first:
+                        bank.set_pipeline(second)
+                vo = torch.full((V, fr), float("nan"), device="cuda")
+                bank.render(fr, vo, fr, None)
+                bank.sync()
+                outs.append(vo.cpu().numpy())
+            return np.concatenate(outs, axis=1), bank.get_state()
+
+    a = run(1, 1)
+    for first, second in ((4, 4), (4, 2), (4, 1), (1, 4)):
+        b = run(first, second)
+        assert a[0].tobytes() == b[0].tobytes(), (first, second)
+        assert a[1].tobytes() == b[1].tobytes(), (first, second)
+
+
 def test_pipelined_back_to_back_without_sync():
     """Many blocks enqueued without a host sync in between (the bench shape), joined at the end."""
     V, T, N = 4096, 1024, 24
