@@ -291,7 +291,8 @@ EXAMPLE_SYNTH2 = "synth mySynth {\n\n}\n"          # the reference's example.syn
 
 def test_moving_cutoff_functions_on_cpu(tmp_path):
     """synth2_b200/csrc/s2_cutoff.h compiles for the CPU: the straight-line division, e^-theta, the windowed
-    sin / cos, a whole decay sweep at the worst corner and the 4-frame interpolation (tools/check_cutoff.cpp)."""
+    sin / cos, the division by the sample rate (every numerator at the usual rates), 2^x around a window centre and
+    a whole decay sweep at the worst corner against the full evaluation (tools/check_cutoff.cpp)."""
     import shutil
     import subprocess
     if not shutil.which("g++"):
