@@ -279,6 +279,12 @@ def parity_of_timed_render(voices, final_state, last_block, frames, np):
     peak = float(np.max(np.abs(ref)))
     p_err, p_ref = float(np.sum(err * err)), float(np.sum(ref.astype(np.float64) ** 2))
     snr = float("inf") if p_err == 0.0 else 10.0 * float(np.log10(max(p_ref, 1e-300) / p_err))
+    def sample(mask):
+        e, r = err[mask], ref[mask].astype(np.float64)
+        pe, pr = float(np.sum(e * e)), float(np.sum(r * r))
+        return {"voices": int(mask.sum()), "max_abs_err": float(e.max()) if e.size else 0.0,
+                "snr_db": float("inf") if pe == 0.0 else 10.0 * float(np.log10(max(pr, 1e-300) / pe))}
+    in_corner = np.isin(idx, corner)
     gs = final_state[idx]
     over = [{"voice": int(idx[i]), "cutoff_hz": float(sub["lpf_freq_hz"][i]), "damping": float(sub["damping"][i]),
              "max_abs_err": float(per_voice[i])} for i in np.argsort(-per_voice)[:8] if per_voice[i] > 1e-4]
@@ -287,6 +293,9 @@ def parity_of_timed_render(voices, final_state, last_block, frames, np):
             "frame_offset_equal": bool(np.array_equal(gs["frame_offset"], st["frame_offset"])),
             "max_abs_err": float(per_voice.max()), "ref_peak": peak,
             "max_abs_err_over_ref_peak": float(per_voice.max()) / max(peak, 1e-30), "snr_db": snr,
+            # the two halves of the sample apart: voices spread over the bank, and the low-cutoff x low-damping corner
+            # where one ulp of cutoff moves the reference itself by several 1e-4
+            "spread_sample": sample(~in_corner), "corner_sample": sample(in_corner),
             "voices_over_1e-4_unscaled": over, "oracle_seconds": dt}
 
 
